@@ -1,0 +1,223 @@
+"""Host-side mirror of the C ABI: `Localizer` wraps an at_context; `dropin` exposes the
+reference-named per-frame functions (rolling_buffer_write_out, buffer_window, correlations_init,
+...) on numpy views of the reference structs.  No compute happens in Python."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+NL_REF = 93
+CORR_DT = np.dtype([("correlations", np.int64, (NL_REF,)), ("best_shift", np.int32), ("_pad", np.int32),
+                    ("last_update", np.uint64)])
+BUFFER_DT = np.dtype([("buffer", np.int16, (1024,)), ("power", np.int64)])
+RING_DT = np.dtype([("head", np.int32), ("_pad0", np.int32), ("incoming_power", np.int64),
+                    ("incoming_total", np.int64), ("outgoing_power", np.int64),
+                    ("outgoing_total", np.int64), ("is_full", np.uint8), ("_pad1", np.uint8),
+                    ("buffer", np.int16, (1024,)), ("_pad2", np.uint8, (6,))])
+
+_ALL = ("lags", "corr", "raw", "cell", "highest", "xy", "gate", "classes", "windowed", "power")
+
+
+def _np_ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Localizer:
+    """One at_context: a shape (mics, frame length, lag range), its tables and streams on one GPU."""
+
+    def __init__(self, device=0, n_mics=3, n_bits=10, max_shift=46, kernel="auto", mic_xy=None,
+                 sample_rate_hz=50000.0, speed_of_sound=343.0, half_w=50, half_h=50, px_per_m=24.0,
+                 height_m=1.2):
+        self.lib = L.load()
+        cfg = L.AtConfig()
+        self.lib.at_config_reference(C.byref(cfg))
+        cfg.device, cfg.n_mics, cfg.n_bits, cfg.max_shift = device, n_mics, n_bits, max_shift
+        cfg.kernel = L.KERNELS[kernel]
+        cfg.sample_rate_hz, cfg.speed_of_sound = sample_rate_hz, speed_of_sound
+        cfg.half_w, cfg.half_h, cfg.px_per_m, cfg.height_m = half_w, half_h, px_per_m, height_m
+        if mic_xy is not None:
+            xy = np.asarray(mic_xy, np.float32).reshape(n_mics, 2)
+            cfg.use_reference_triangle = 0
+            for m in range(n_mics):
+                cfg.mic_xy[m][0], cfg.mic_xy[m][1] = float(xy[m, 0]), float(xy[m, 1])
+        elif n_mics != 3:   # our choice (the reference has no other geometry): circle of radius 0.1 m
+            cfg.use_reference_triangle = 0
+            for m in range(min(n_mics, L.AT_MAX_MICS)):
+                ang = 2.0 * np.pi * m / n_mics
+                cfg.mic_xy[m][0], cfg.mic_xy[m][1] = float(np.float32(0.1 * np.cos(ang))), float(np.float32(0.1 * np.sin(ang)))
+        self.cfg = cfg
+        self.ctx = C.c_void_p()
+        L.check(self.lib.at_create(C.byref(cfg), C.byref(self.ctx)))
+        v = [C.c_int32() for _ in range(5)]
+        L.check(self.lib.at_shape(self.ctx, *[C.byref(x) for x in v]))
+        self.n_mics, self.n_samples, self.n_pairs, self.n_lags, self.n_cells = [x.value for x in v]
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None) and self.ctx.value:
+            self.lib.at_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- geometry products
+    def mics(self):
+        xy = np.zeros((self.n_mics, 2), np.float32)
+        L.check(self.lib.at_get_mics(self.ctx, _np_ptr(xy)))
+        return xy
+
+    def lut(self):
+        lut = np.zeros((self.n_pairs, self.n_cells), np.uint8)
+        L.check(self.lib.at_get_lut(self.ctx, _np_ptr(lut)))
+        return lut
+
+    # ---- output allocation
+    def _shapes(self, F, struct_corr):
+        P, NL, M, N = self.n_pairs, self.n_lags, self.n_mics, self.n_samples
+        return {"lags": ((F, P), "int32"), "corr": ((F, P, NL + 2 if struct_corr else NL), "int64"),
+                "raw": ((F, P, NL), "int64"), "cell": ((F,), "int32"), "highest": ((F,), "int64"),
+                "xy": ((F, 2), "float32"), "gate": ((F,), "uint8"), "classes": ((F, self.n_cells), "uint8"),
+                "windowed": ((F, M, N), "int16"), "power": ((F, M), "int64")}
+
+    # ---- batched path, device-resident (torch tensors)
+    def localize_device(self, adc, heads=None, want=("lags",), out=None, struct_corr=False, stream=None):
+        """adc: torch.uint8 CUDA tensor [F, mics, N] (ring order).  Returns dict of CUDA tensors.
+        Asynchronous on `stream` (a torch.cuda.Stream; default: the current torch stream)."""
+        import torch
+        assert adc.is_cuda and adc.dtype == torch.uint8 and adc.is_contiguous()
+        F = adc.shape[0]
+        assert adc.numel() == F * self.n_mics * self.n_samples
+        shapes = self._shapes(F, struct_corr)
+        res = {} if out is None else out
+        o = L.AtOutputs()
+        o.corr_layout = L.AT_CORR_STRUCT if struct_corr else L.AT_CORR_PACKED
+        for k in want:
+            if k not in res:
+                res[k] = torch.empty(shapes[k][0], dtype=getattr(torch, shapes[k][1]), device=adc.device)
+            setattr(o, k, res[k].data_ptr())
+        st = stream if stream is not None else torch.cuda.current_stream(adc.device)
+        hp = None if heads is None else C.c_void_p(heads.data_ptr())
+        L.check(self.lib.at_localize_device(self.ctx, C.c_void_p(adc.data_ptr()), hp, F, C.byref(o),
+                                            C.c_void_p(st.cuda_stream)))
+        return res
+
+    # ---- batched path from host memory (numpy arrays or pinned torch CPU tensors)
+    def localize_host(self, adc, heads=None, want=("lags",), out=None, struct_corr=False):
+        F = adc.shape[0]
+        shapes = self._shapes(F, struct_corr)
+        res = {} if out is None else out
+        o = L.AtOutputs()
+        o.corr_layout = L.AT_CORR_STRUCT if struct_corr else L.AT_CORR_PACKED
+        for k in want:
+            if k not in res:
+                res[k] = np.empty(shapes[k][0], dtype=shapes[k][1])
+            setattr(o, k, _host_ptr(res[k]))
+        L.check(self.lib.at_localize_host(self.ctx, C.c_void_p(_host_ptr(adc)),
+                                          None if heads is None else C.c_void_p(_host_ptr(heads)), F, C.byref(o)))
+        return res
+
+    def synchronize(self):
+        L.check(self.lib.at_synchronize(self.ctx))
+
+    # ---- temporal stage / likelihood map on device arrays
+    def average_device(self, est, est_best, est_time, fresh, gate, now_us, stream=None):
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(est.device)
+        A = est.shape[0]
+        L.check(self.lib.at_average_device(self.ctx, est.data_ptr(), est_best.data_ptr(), est_time.data_ptr(),
+                                           fresh.data_ptr(), None if gate is None else gate.data_ptr(), A,
+                                           int(now_us), C.c_void_p(st.cuda_stream)))
+
+    def heatmap_device(self, corr, want=("cell", "highest"), stream=None):
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(corr.device)
+        A = corr.shape[0]
+        shapes = self._shapes(A, False)
+        res = {k: torch.empty(shapes[k][0], dtype=getattr(torch, shapes[k][1]), device=corr.device) for k in want}
+        g = lambda k: res[k].data_ptr() if k in res else None  # noqa: E731
+        L.check(self.lib.at_heatmap_device(self.ctx, corr.data_ptr(), A, g("cell"), g("highest"), g("xy"),
+                                           g("classes"), C.c_void_p(st.cuda_stream)))
+        return res
+
+    # ---- synthetic frames
+    def synth_host(self, n_frames, seed=0xA7D10, flags=0, first_frame=0):
+        adc = np.empty((n_frames, self.n_mics, self.n_samples), np.uint8)
+        heads = np.empty(n_frames, np.int32)
+        cells = np.empty(n_frames, np.int32)
+        L.check(self.lib.at_synth_host(self.ctx, seed, flags, first_frame, n_frames, _np_ptr(adc), _np_ptr(heads),
+                                       _np_ptr(cells)))
+        return adc, heads, cells
+
+    def synth_device(self, n_frames, seed=0xA7D10, flags=0, first_frame=0, out=None, stream=None):
+        import torch
+        dev = torch.device("cuda", self.device)
+        adc = out if out is not None else torch.empty((n_frames, self.n_mics, self.n_samples), dtype=torch.uint8, device=dev)
+        heads = torch.empty(n_frames, dtype=torch.int32, device=dev)
+        cells = torch.empty(n_frames, dtype=torch.int32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        L.check(self.lib.at_synth_device(self.ctx, seed, flags, first_frame, n_frames, adc.data_ptr(), heads.data_ptr(),
+                                         cells.data_ptr(), C.c_void_p(st.cuda_stream)))
+        return adc, heads, cells
+
+    def microbench(self, which):
+        g, mhz = C.c_double(), C.c_double()
+        L.check(self.lib.at_microbench(self.ctx, L.UBENCH[which], C.byref(g), C.byref(mhz)))
+        return g.value, mhz.value
+
+    def kernel_launches(self):
+        return int(self.lib.at_kernel_launches())
+
+
+def _host_ptr(a):
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    assert not a.is_cuda and a.is_contiguous()   # torch CPU tensor (pinned or not)
+    return a.data_ptr()
+
+
+class _DropIn:
+    """The reference-named entry points on numpy structured scalars (RING_DT / BUFFER_DT / CORR_DT)."""
+
+    def __init__(self):
+        self._lib = None
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            self._lib = L.load()
+        return self._lib
+
+    @staticmethod
+    def _p(rec):
+        return C.c_void_p(rec.ctypes.data)
+
+    def new_ring(self):
+        r = np.zeros(1, RING_DT)
+        self.lib.rolling_buffer_init(self._p(r))
+        return r
+
+    def rolling_buffer_init(self, r): self.lib.rolling_buffer_init(self._p(r))
+    def rolling_buffer_push(self, r, s): self.lib.rolling_buffer_push(self._p(r), int(s))
+    def rolling_buffer_write_out(self, r, b): self.lib.rolling_buffer_write_out(self._p(r), self._p(b))
+    def rolling_buffer_get_incoming_power(self, r): return int(self.lib.rolling_buffer_get_incoming_power(self._p(r)))
+    def rolling_buffer_get_outgoing_power(self, r): return int(self.lib.rolling_buffer_get_outgoing_power(self._p(r)))
+    def buffer_normalize_range(self, b): self.lib.buffer_normalize_range(self._p(b))
+    def buffer_window(self, b): self.lib.buffer_window(self._p(b))
+    def correlations_init(self, c, a, b): self.lib.correlations_init(self._p(c), self._p(a), self._p(b))
+    def correlations_average(self, e, n): self.lib.correlations_average(self._p(e), self._p(n))
+    def set_time_us(self, t): self.lib.at_set_time_us(int(t))
+
+    def microphones_init(self):
+        self.lib.microphones_init()
+        pt = (C.c_float * 2)
+        return np.array([list(pt.in_dll(self.lib, n)) for n in ("mic_a_location", "mic_b_location", "mic_c_location")],
+                        np.float32)
+
+
+dropin = _DropIn()

@@ -1,0 +1,624 @@
+// at_api.cu -- host side of libat_b200.so: context, tables, the batched C ABI and the drop-in
+// symbols of include/at_b200.h.  There is no CPU implementation of any compute stage in here:
+// without a usable sm_100 device every entry point fails (batched API: AT_ENOGPU; drop-in
+// symbols: abort with a message).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <atomic>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/at_b200.h"
+#include "at_internal.h"
+#include "at_synth.h"
+#include "at_window_tables.h"
+
+// ------------------------------------------------------------------ errors, counters, clock
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void at_count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(AT_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *at_last_error(void) { return g_err; }
+extern "C" uint64_t at_kernel_launches(void) { return g_launches.load(); }
+
+// The harness may supply the SDK clock symbol the reference uses (correlations.c:35, :40).
+extern "C" absolute_time_t get_absolute_time(void) __attribute__((weak));
+static std::atomic<uint64_t> g_pinned_time{UINT64_MAX};
+extern "C" void at_set_time_us(uint64_t now_us) { g_pinned_time.store(now_us); }
+extern "C" uint64_t at_get_time_us(void)
+{
+    if (get_absolute_time) return get_absolute_time();
+    const uint64_t p = g_pinned_time.load();
+    if (p != UINT64_MAX) return p;
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (uint64_t)ts.tv_sec * 1000000ull + (uint64_t)ts.tv_nsec / 1000ull;
+}
+
+// ------------------------------------------------------------------ context
+struct HostSlot {
+    cudaStream_t stream = nullptr;
+    size_t cap_frames = 0;
+    uint8_t *adc = nullptr; int32_t *heads = nullptr;
+    int32_t *lags = nullptr; void *corr = nullptr; long long *raw = nullptr; int32_t *cell = nullptr;
+    long long *highest = nullptr; float *xy = nullptr; uint8_t *gate = nullptr; uint8_t *classes = nullptr;
+    int16_t *windowed = nullptr; long long *power = nullptr;
+};
+
+struct at_context {
+    at_config cfg;
+    int sm_count = 0;
+    int n_pairs = 0, n_samples = 0, n_lags = 0, n_cells = 0, n_cand = 0;
+    cudaStream_t stream = nullptr;
+    // device tables
+    float *d_mic_xy = nullptr; uint8_t *d_lut = nullptr; uint8_t *d_cand_idx = nullptr; int32_t *d_cand_cell = nullptr;
+    int16_t *d_window = nullptr; float *d_gauss = nullptr; int32_t *d_delay_q8 = nullptr;
+    // host copies
+    std::vector<float> h_mic_xy; std::vector<uint8_t> h_lut; std::vector<int32_t> h_delay_q8;
+    // staging for the host API and the drop-in symbols
+    HostSlot slot[2];
+    void *d_scratch = nullptr; size_t scratch_bytes = 0;
+};
+
+static int ensure(void **p, size_t bytes)
+{
+    if (*p) return AT_OK;
+    CU(cudaMalloc(p, bytes));
+    return AT_OK;
+}
+
+extern "C" void at_config_reference(at_config *c)
+{
+    memset(c, 0, sizeof *c);
+    c->device = 0; c->n_mics = 3; c->n_bits = 10; c->max_shift = 46; c->kernel = AT_KERNEL_AUTO;
+    c->sample_rate_hz = 50000.f; c->speed_of_sound = 343.0f;
+    c->half_w = 50; c->half_h = 50; c->px_per_m = 24.0f; c->height_m = 1.2f;
+    c->use_reference_triangle = 1;
+}
+
+static const int16_t *pick_window(int n_bits, std::vector<int16_t> &out)
+{
+    const int n = 1 << n_bits;
+    out.resize(n);
+    if (n_bits <= 10) {          // ref: components/buffer.c:8 -- shorter frames decimate the 1024 table
+        const int step = 10 - n_bits;
+        for (int i = 0; i < n; i++) out[i] = AT_WINDOW_1024[i << step];
+    } else {                     // no reference counterpart: notebook recipe at 4096
+        const int step = 12 - n_bits;
+        for (int i = 0; i < n; i++) out[i] = AT_WINDOW_4096[i << step];
+    }
+    return out.data();
+}
+
+extern "C" void at_destroy(at_context *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    for (auto &s : c->slot) {
+        void *ptrs[] = {s.adc, s.heads, s.lags, s.corr, s.raw, s.cell, s.highest, s.xy, s.gate, s.classes, s.windowed, s.power};
+        for (void *p : ptrs) if (p) cudaFree(p);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int create_impl(const at_config *cfg, at_context *c)
+{
+    c->cfg = *cfg;
+    const int M = cfg->n_mics, L = cfg->max_shift;
+    if (M < 2 || M > AT_MAX_MICS || cfg->n_bits < 8 || cfg->n_bits > 12 || L < 1 || L > 127 ||
+        cfg->half_w < 0 || cfg->half_h < 0 || cfg->half_w > 512 || cfg->half_h > 512)
+        return fail(AT_EINVAL, "unsupported shape: mics=%d n_bits=%d max_shift=%d", M, cfg->n_bits, L);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device)
+        return fail(AT_ENOGPU, "no CUDA device %d (found %d): libat_b200 has no CPU fallback", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(AT_ENOGPU, "device %d is sm_%d%d; this library carries sm_100a code only", cfg->device, prop.major, prop.minor);
+    c->sm_count = prop.multiProcessorCount;
+    c->n_pairs = M * (M - 1) / 2;
+    c->n_samples = 1 << cfg->n_bits;
+    c->n_lags = 2 * L + 1;
+    c->n_cells = (2 * cfg->half_w + 1) * (2 * cfg->half_h + 1);
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &s : c->slot) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+
+    // geometry (ref: microphones.c) and lag LUT (ref: vga_heatmap.h:50-92), both on the device
+    CU(cudaMalloc(&c->d_mic_xy, sizeof(float) * 2 * AT_MAX_MICS));
+    if (M == 3 && cfg->use_reference_triangle) {
+        CU(at_launch_mics_triangle(0.132f, 0.15f, 0.20f, 1, c->d_mic_xy, c->stream));   // constants.h:17-19, :26
+    } else {
+        CU(cudaMemcpyAsync(c->d_mic_xy, cfg->mic_xy, sizeof(float) * 2 * M, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaMalloc(&c->d_lut, (size_t)c->n_pairs * c->n_cells));
+    CU(at_launch_lut_build(c->d_mic_xy, M, L, cfg->sample_rate_hz, cfg->speed_of_sound, cfg->half_w, cfg->half_h,
+                           cfg->px_per_m, cfg->height_m, c->d_lut, c->stream));
+    c->h_mic_xy.resize(2 * M);
+    c->h_lut.resize((size_t)c->n_pairs * c->n_cells);
+    CU(cudaMemcpyAsync(c->h_mic_xy.data(), c->d_mic_xy, sizeof(float) * 2 * M, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_lut.data(), c->d_lut, c->h_lut.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+
+    // distinct lag-index tuples, in order of first row-major appearance (index bookkeeping only)
+    {
+        std::unordered_map<std::string, int> seen;
+        std::vector<int32_t> first_cell;
+        std::vector<std::string> keys;
+        std::string key((size_t)c->n_pairs, '\0');
+        for (int cell = 0; cell < c->n_cells; cell++) {
+            for (int p = 0; p < c->n_pairs; p++) key[p] = (char)c->h_lut[(size_t)p * c->n_cells + cell];
+            if (seen.emplace(key, (int)keys.size()).second) { keys.push_back(key); first_cell.push_back(cell); }
+        }
+        c->n_cand = (int)keys.size();
+        std::vector<uint8_t> idx((size_t)c->n_pairs * c->n_cand);
+        for (int t = 0; t < c->n_cand; t++)
+            for (int p = 0; p < c->n_pairs; p++) idx[(size_t)p * c->n_cand + t] = (uint8_t)keys[t][p];
+        CU(cudaMalloc(&c->d_cand_idx, idx.size()));
+        CU(cudaMalloc(&c->d_cand_cell, sizeof(int32_t) * c->n_cand));
+        CU(cudaMemcpy(c->d_cand_idx, idx.data(), idx.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_cand_cell, first_cell.data(), sizeof(int32_t) * c->n_cand, cudaMemcpyHostToDevice));
+    }
+
+    // window table for this frame length
+    {
+        std::vector<int16_t> w;
+        pick_window(cfg->n_bits, w);
+        CU(cudaMalloc(&c->d_window, sizeof(int16_t) * w.size()));
+        CU(cudaMemcpy(c->d_window, w.data(), sizeof(int16_t) * w.size(), cudaMemcpyHostToDevice));
+    }
+    // Gaussian factors exp(-d^2/36) for d = 0..2L with the host libm, exactly as
+    // correlations.c:30 evaluates them (float division, double exp, rounded to float).
+    {
+        std::vector<float> g(2 * L + 1);
+        for (int d = 0; d <= 2 * L; d++) g[d] = (float)exp((double)((float)(-(d * d)) / 36.f));
+        CU(cudaMalloc(&c->d_gauss, sizeof(float) * g.size()));
+        CU(cudaMemcpy(c->d_gauss, g.data(), sizeof(float) * g.size(), cudaMemcpyHostToDevice));
+    }
+    // synthetic-source propagation delays per cell and mic, Q8 samples relative to the sphere radius
+    {
+        const int W = 2 * cfg->half_w + 1;
+        c->h_delay_q8.resize((size_t)c->n_cells * M);
+        for (int cell = 0; cell < c->n_cells; cell++) {
+            double x = (cell % W - cfg->half_w) / (double)cfg->px_per_m;
+            double y = (cfg->half_h - cell / W) / (double)cfg->px_per_m;
+            double z = cfg->height_m;
+            const double k = cfg->height_m / sqrt(x * x + y * y + z * z);
+            x *= k; y *= k; z *= k;
+            for (int m = 0; m < M; m++) {
+                const double dx = x - c->h_mic_xy[2 * m], dy = y - c->h_mic_xy[2 * m + 1];
+                const double dist = sqrt(dx * dx + dy * dy + z * z);
+                c->h_delay_q8[(size_t)cell * M + m] =
+                    (int32_t)llround(256.0 * (dist - cfg->height_m) / cfg->speed_of_sound * cfg->sample_rate_hz);
+            }
+        }
+        CU(cudaMalloc(&c->d_delay_q8, sizeof(int32_t) * c->h_delay_q8.size()));
+        CU(cudaMemcpy(c->d_delay_q8, c->h_delay_q8.data(), sizeof(int32_t) * c->h_delay_q8.size(), cudaMemcpyHostToDevice));
+    }
+    c->scratch_bytes = 1 << 16;
+    CU(cudaMalloc(&c->d_scratch, c->scratch_bytes));
+    return AT_OK;
+}
+
+extern "C" int at_create(const at_config *cfg, at_context **out)
+{
+    if (!cfg || !out) return fail(AT_EINVAL, "at_create: null argument");
+    at_context *c = new at_context();
+    const int rc = create_impl(cfg, c);
+    if (rc != AT_OK) { at_destroy(c); *out = nullptr; return rc; }
+    *out = c;
+    return AT_OK;
+}
+
+extern "C" int at_get_mics(const at_context *c, float *xy)
+{
+    if (!c || !xy) return fail(AT_EINVAL, "at_get_mics: null argument");
+    memcpy(xy, c->h_mic_xy.data(), sizeof(float) * c->h_mic_xy.size());
+    return AT_OK;
+}
+extern "C" int at_get_lut(const at_context *c, uint8_t *lut)
+{
+    if (!c || !lut) return fail(AT_EINVAL, "at_get_lut: null argument");
+    memcpy(lut, c->h_lut.data(), c->h_lut.size());
+    return AT_OK;
+}
+extern "C" int at_shape(const at_context *c, int32_t *n_mics, int32_t *n_samples, int32_t *n_pairs, int32_t *n_lags,
+                        int32_t *n_cells)
+{
+    if (!c) return fail(AT_EINVAL, "at_shape: null context");
+    if (n_mics) *n_mics = c->cfg.n_mics;
+    if (n_samples) *n_samples = c->n_samples;
+    if (n_pairs) *n_pairs = c->n_pairs;
+    if (n_lags) *n_lags = c->n_lags;
+    if (n_cells) *n_cells = c->n_cells;
+    return AT_OK;
+}
+extern "C" int at_synchronize(at_context *c)
+{
+    if (!c) return fail(AT_EINVAL, "at_synchronize: null context");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto &s : c->slot) CU(cudaStreamSynchronize(s.stream));
+    return AT_OK;
+}
+
+// ------------------------------------------------------------------ fused path, device API
+static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int kernel, cudaStream_t st)
+{
+    p.window = c->d_window; p.gauss = c->d_gauss; p.lut = c->d_lut;
+    p.cand_idx = c->d_cand_idx; p.cand_cell = c->d_cand_cell;
+    p.n_cand = c->n_cand; p.n_cells = c->n_cells; p.half_w = c->cfg.half_w; p.half_h = c->cfg.half_h;
+    p.px_per_m = c->cfg.px_per_m;
+    if (kernel == AT_KERNEL_AUTO) kernel = at_fused_imma_supports(sh) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;
+    cudaError_t e;
+    if (kernel == AT_KERNEL_IMMA) {
+        if (!at_fused_imma_supports(sh)) return fail(AT_EINVAL, "IMMA kernel has no instantiation for this shape");
+        e = at_launch_fused_imma(sh, p, c->sm_count, st);
+    } else {
+        e = at_launch_fused_imad(sh, p, c->sm_count, st);
+    }
+    if (e == cudaErrorInvalidValue) return fail(AT_EINVAL, "no kernel instantiation for mics=%d n_bits=%d L=%d", sh.n_mics, sh.n_bits, sh.max_shift);
+    if (e != cudaSuccess) return fail(AT_ECUDA, "fused kernel launch: %s", cudaGetErrorString(e));
+    return AT_OK;
+}
+
+extern "C" int at_localize_device(at_context *c, const uint8_t *d_adc, const int32_t *d_heads, size_t n_frames,
+                                  const at_outputs *o, void *stream)
+{
+    if (!c || !o || (!d_adc && n_frames)) return fail(AT_EINVAL, "at_localize_device: null argument");
+    if (o->corr && o->corr_layout == AT_CORR_STRUCT && c->n_lags != CORRELATION_BUFFER_SIZE)
+        return fail(AT_EINVAL, "AT_CORR_STRUCT needs 93 lags");
+    if (n_frames == 0) return AT_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    AtFusedParams p;
+    memset(&p, 0, sizeof p);
+    p.adc = d_adc; p.heads = d_heads; p.n_frames = n_frames;
+    p.lags = o->lags; p.corr = o->corr; p.corr_struct = o->corr_layout == AT_CORR_STRUCT;
+    p.raw = (long long *)o->raw; p.cell = o->cell; p.highest = (long long *)o->highest; p.xy = o->xy;
+    p.gate = o->gate; p.classes = o->classes; p.windowed = o->windowed; p.power = (long long *)o->power;
+    p.now_us = at_get_time_us();
+    const AtShape sh = {c->cfg.n_mics, c->cfg.n_bits, c->cfg.max_shift};
+    return launch_fused(c, sh, p, c->cfg.kernel, stream ? (cudaStream_t)stream : c->stream);
+}
+
+// ------------------------------------------------------------------ fused path, host API
+static size_t chunk_frames(const at_context *c)
+{
+    const char *env = getenv("AT_CHUNK_FRAMES");
+    size_t n = env ? (size_t)strtoull(env, nullptr, 10) : 0;
+    if (!n) n = ((size_t)48 << 20) / ((size_t)c->cfg.n_mics * c->n_samples);   // ~48 MiB of ADC bytes per chunk
+    return n ? n : 1;
+}
+
+static int host_async(at_context *c, const uint8_t *h_adc, const int32_t *h_heads, size_t n_frames, const at_outputs *o)
+{
+    CU(cudaSetDevice(c->cfg.device));
+    const size_t M = c->cfg.n_mics, N = c->n_samples, P = c->n_pairs, NL = c->n_lags, cells = c->n_cells;
+    const size_t C = chunk_frames(c);
+    const size_t corr_bytes = o->corr_layout == AT_CORR_STRUCT ? P * sizeof(struct correlations_t) : P * NL * 8;
+    if (o->corr && o->corr_layout == AT_CORR_STRUCT && NL != CORRELATION_BUFFER_SIZE)
+        return fail(AT_EINVAL, "AT_CORR_STRUCT needs 93 lags");
+    for (auto &s : c->slot) {
+        if (s.cap_frames != C) {
+            void **ptrs[] = {(void **)&s.adc, (void **)&s.heads, (void **)&s.lags, &s.corr, (void **)&s.raw, (void **)&s.cell,
+                             (void **)&s.highest, (void **)&s.xy, (void **)&s.gate, (void **)&s.classes,
+                             (void **)&s.windowed, (void **)&s.power};
+            CU(cudaStreamSynchronize(s.stream));
+            for (void **p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+            s.cap_frames = C;
+        }
+        int rc = ensure((void **)&s.adc, C * M * N);
+        if (rc == AT_OK && h_heads) rc = ensure((void **)&s.heads, C * 4);
+        if (rc == AT_OK && o->lags) rc = ensure((void **)&s.lags, C * P * 4);
+        if (rc == AT_OK && o->corr) rc = ensure(&s.corr, C * P * sizeof(struct correlations_t) > C * P * NL * 8 ? C * P * sizeof(struct correlations_t) : C * P * NL * 8);
+        if (rc == AT_OK && o->raw) rc = ensure((void **)&s.raw, C * P * NL * 8);
+        if (rc == AT_OK && o->cell) rc = ensure((void **)&s.cell, C * 4);
+        if (rc == AT_OK && o->highest) rc = ensure((void **)&s.highest, C * 8);
+        if (rc == AT_OK && o->xy) rc = ensure((void **)&s.xy, C * 8);
+        if (rc == AT_OK && o->gate) rc = ensure((void **)&s.gate, C);
+        if (rc == AT_OK && o->classes) rc = ensure((void **)&s.classes, C * cells);
+        if (rc == AT_OK && o->windowed) rc = ensure((void **)&s.windowed, C * M * N * 2);
+        if (rc == AT_OK && o->power) rc = ensure((void **)&s.power, C * M * 8);
+        if (rc != AT_OK) return rc;
+    }
+    const AtShape sh = {c->cfg.n_mics, c->cfg.n_bits, c->cfg.max_shift};
+    size_t k = 0;
+    for (size_t f0 = 0; f0 < n_frames; f0 += C, k++) {
+        HostSlot &s = c->slot[k & 1];
+        const size_t n = n_frames - f0 < C ? n_frames - f0 : C;
+        CU(cudaMemcpyAsync(s.adc, h_adc + f0 * M * N, n * M * N, cudaMemcpyHostToDevice, s.stream));
+        if (h_heads) CU(cudaMemcpyAsync(s.heads, h_heads + f0, n * 4, cudaMemcpyHostToDevice, s.stream));
+        AtFusedParams p;
+        memset(&p, 0, sizeof p);
+        p.adc = s.adc; p.heads = h_heads ? s.heads : nullptr; p.n_frames = n;
+        p.lags = o->lags ? s.lags : nullptr; p.corr = o->corr ? s.corr : nullptr;
+        p.corr_struct = o->corr_layout == AT_CORR_STRUCT;
+        p.raw = o->raw ? s.raw : nullptr; p.cell = o->cell ? s.cell : nullptr; p.highest = o->highest ? s.highest : nullptr;
+        p.xy = o->xy ? s.xy : nullptr; p.gate = o->gate ? s.gate : nullptr; p.classes = o->classes ? s.classes : nullptr;
+        p.windowed = o->windowed ? s.windowed : nullptr; p.power = o->power ? s.power : nullptr;
+        p.now_us = at_get_time_us();
+        const int rc = launch_fused(c, sh, p, c->cfg.kernel, s.stream);
+        if (rc != AT_OK) return rc;
+#define D2H(field, dst, bytes_per_frame)                                                                   \
+    if (dst) CU(cudaMemcpyAsync((char *)(dst) + f0 * (bytes_per_frame), s.field, n * (bytes_per_frame),    \
+                                cudaMemcpyDeviceToHost, s.stream));
+        D2H(lags, o->lags, P * 4)
+        D2H(corr, o->corr, corr_bytes)
+        D2H(raw, o->raw, P * NL * 8)
+        D2H(cell, o->cell, 4)
+        D2H(highest, o->highest, 8)
+        D2H(xy, o->xy, 8)
+        D2H(gate, o->gate, 1)
+        D2H(classes, o->classes, cells)
+        D2H(windowed, o->windowed, M * N * 2)
+        D2H(power, o->power, M * 8)
+#undef D2H
+    }
+    return AT_OK;
+}
+
+extern "C" int at_localize_host(at_context *c, const uint8_t *h_adc, const int32_t *h_heads, size_t n_frames,
+                                const at_outputs *o)
+{
+    if (!c || !o || (!h_adc && n_frames)) return fail(AT_EINVAL, "at_localize_host: null argument");
+    if (!n_frames) return AT_OK;
+    const int rc = host_async(c, h_adc, h_heads, n_frames, o);
+    if (rc != AT_OK) return rc;
+    for (auto &s : c->slot) CU(cudaStreamSynchronize(s.stream));
+    return AT_OK;
+}
+
+extern "C" int at_localize_host_sharded(at_context **ctxs, int n_ctx, const uint8_t *h_adc, const int32_t *h_heads,
+                                        size_t n_frames, const at_outputs *o)
+{
+    if (!ctxs || n_ctx < 1 || !o) return fail(AT_EINVAL, "at_localize_host_sharded: bad argument");
+    for (int g = 0; g < n_ctx; g++) {
+        at_context *c = ctxs[g];
+        const size_t lo = n_frames * g / n_ctx, hi = n_frames * (g + 1) / n_ctx;
+        if (hi == lo) continue;
+        const size_t M = c->cfg.n_mics, N = c->n_samples, P = c->n_pairs, NL = c->n_lags;
+        const size_t corr_bytes = o->corr_layout == AT_CORR_STRUCT ? P * sizeof(struct correlations_t) : P * NL * 8;
+        at_outputs sub = *o;
+#define OFF(field, bytes) if (sub.field) sub.field = (decltype(sub.field))((char *)sub.field + lo * (bytes));
+        OFF(lags, P * 4) OFF(corr, corr_bytes) OFF(raw, P * NL * 8) OFF(cell, 4) OFF(highest, 8) OFF(xy, 8)
+        OFF(gate, 1) OFF(classes, (size_t)c->n_cells) OFF(windowed, M * N * 2) OFF(power, M * 8)
+#undef OFF
+        const int rc = host_async(c, h_adc + lo * M * N, h_heads ? h_heads + lo : nullptr, hi - lo, &sub);
+        if (rc != AT_OK) return rc;
+    }
+    for (int g = 0; g < n_ctx; g++) {
+        CU(cudaSetDevice(ctxs[g]->cfg.device));
+        for (auto &s : ctxs[g]->slot) CU(cudaStreamSynchronize(s.stream));
+    }
+    return AT_OK;
+}
+
+// ------------------------------------------------------------------ temporal average, likelihood map
+extern "C" int at_average_device(at_context *c, int64_t *d_est, int32_t *d_est_best, uint64_t *d_est_time,
+                                 const int64_t *d_fresh, const uint8_t *d_gate, size_t n_arrays, uint64_t now_us,
+                                 void *stream)
+{
+    if (!c || !d_est || !d_est_best || !d_est_time || !d_fresh) return fail(AT_EINVAL, "at_average_device: null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(at_launch_average((long long *)d_est, d_est_best, (unsigned long long *)d_est_time, (const long long *)d_fresh,
+                         d_gate, n_arrays, c->n_pairs, c->cfg.max_shift, now_us, nullptr,
+                         stream ? (cudaStream_t)stream : c->stream));
+    return AT_OK;
+}
+
+extern "C" int at_heatmap_device(at_context *c, const int64_t *d_corr, size_t n_arrays, int32_t *d_cell,
+                                 int64_t *d_highest, float *d_xy, uint8_t *d_classes, void *stream)
+{
+    if (!c || !d_corr) return fail(AT_EINVAL, "at_heatmap_device: null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(at_launch_heatmap((const long long *)d_corr, n_arrays, c->n_pairs, c->cfg.max_shift, c->d_lut, c->d_cand_idx,
+                         c->d_cand_cell, c->n_cand, c->n_cells, c->cfg.half_w, c->cfg.half_h, c->cfg.px_per_m, d_cell,
+                         (long long *)d_highest, d_xy, d_classes, stream ? (cudaStream_t)stream : c->stream));
+    return AT_OK;
+}
+
+// ------------------------------------------------------------------ synthetic frames
+extern "C" int at_synth_host(const at_context *c, uint64_t seed, uint32_t flags, size_t first, size_t n_frames,
+                             uint8_t *adc, int32_t *heads, int32_t *true_cell)
+{
+    if (!c || !adc) return fail(AT_EINVAL, "at_synth_host: null argument");
+    const int M = c->cfg.n_mics, N = c->n_samples;
+    for (size_t fl = 0; fl < n_frames; fl++) {
+        const uint64_t f = first + fl;
+        const at_synth_frame fp = at_synth_frame_params(seed, flags, f, c->n_cells, c->cfg.n_bits);
+        for (int m = 0; m < M; m++) {
+            int32_t dq = c->h_delay_q8[(size_t)fp.cell * M + m];
+            if (flags & AT_SYNTH_F_INTEGER_DELAYS) dq = (dq + 128) & ~255;
+            uint8_t *dst = adc + (fl * M + m) * (size_t)N;
+            for (int i = 0; i < N; i++) dst[(fp.head + i) & (N - 1)] = at_synth_sample(seed, f, fp, m, i, dq);
+        }
+        if (heads) heads[fl] = fp.head;
+        if (true_cell) true_cell[fl] = fp.cell;
+    }
+    return AT_OK;
+}
+
+extern "C" int at_synth_device(at_context *c, uint64_t seed, uint32_t flags, size_t first, size_t n_frames,
+                               uint8_t *d_adc, int32_t *d_heads, int32_t *d_true_cell, void *stream)
+{
+    if (!c || !d_adc) return fail(AT_EINVAL, "at_synth_device: null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(at_launch_synth(seed, flags, first, n_frames, c->cfg.n_mics, c->cfg.n_bits, c->n_cells, c->d_delay_q8, d_adc,
+                       d_heads, d_true_cell, stream ? (cudaStream_t)stream : c->stream));
+    return AT_OK;
+}
+
+extern "C" int at_microbench(at_context *c, int which, double *gops, double *sm_mhz_est)
+{
+    if (!c || !gops) return fail(AT_EINVAL, "at_microbench: null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    double mhz = 0;
+    const cudaError_t e = at_run_microbench(which, c->sm_count, gops, &mhz, c->stream);
+    if (e == cudaErrorInvalidValue) return fail(AT_EINVAL, "unknown microbenchmark %d", which);
+    CU(e);
+    if (sm_mhz_est) *sm_mhz_est = mhz;
+    return AT_OK;
+}
+
+// ------------------------------------------------------------------ drop-in symbols
+point2d_t mic_a_location, mic_b_location, mic_c_location;
+static at_context *g_default = nullptr;
+static at_context *g_pair = nullptr;   // 2-channel, one-pair shape behind correlations_init
+
+[[noreturn]] static void die(const char *what)
+{
+    fprintf(stderr, "libat_b200: %s failed: %s\n(no CPU fallback exists; a B200 / sm_100 GPU is required)\n", what, g_err);
+    abort();
+}
+#define CUX(call, what)                                                                    \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) { fail(AT_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); die(what); } \
+    } while (0)
+
+static at_context *default_ctx(void)
+{
+    if (!g_default) {
+        at_config cfg;
+        at_config_reference(&cfg);
+        const char *dev = getenv("AT_DEVICE");
+        if (dev) cfg.device = atoi(dev);
+        if (at_create(&cfg, &g_default) != AT_OK) die("at_create(reference config)");
+        cfg.n_mics = 2; cfg.use_reference_triangle = 0;
+        cfg.mic_xy[0][0] = -0.066f; cfg.mic_xy[1][0] = 0.066f;
+        cfg.kernel = AT_KERNEL_IMAD;
+        if (at_create(&cfg, &g_pair) != AT_OK) die("at_create(pair config)");
+    }
+    cudaSetDevice(g_default->cfg.device);
+    return g_default;
+}
+
+extern "C" void microphones_init(void)
+{
+    at_context *c = default_ctx();
+    mic_a_location.x = c->h_mic_xy[0]; mic_a_location.y = c->h_mic_xy[1];
+    mic_b_location.x = c->h_mic_xy[2]; mic_b_location.y = c->h_mic_xy[3];
+    mic_c_location.x = c->h_mic_xy[4]; mic_c_location.y = c->h_mic_xy[5];
+}
+
+// Capture-side bookkeeping on the caller-owned host struct (see header note); the arithmetic
+// is the reference's recurrence, restated.
+extern "C" void rolling_buffer_init(struct rolling_buffer_t *b) { memset(b, 0, sizeof *b); }
+
+extern "C" void rolling_buffer_push(struct rolling_buffer_t *b, sample_t s)
+{
+    const int h = b->head;
+    const int64_t mid = b->buffer[(h + BUFFER_SIZE / 2) & (BUFFER_SIZE - 1)], old = b->buffer[h];
+    b->outgoing_total += mid - old;
+    b->outgoing_power += mid * mid - old * old;
+    b->incoming_total += (int64_t)s - mid;
+    b->incoming_power += (int64_t)s * s - mid * mid;
+    b->buffer[h] = s;
+    if (h + 1 >= BUFFER_SIZE) { b->head = 0; b->is_full = true; } else b->head = h + 1;
+}
+
+extern "C" power_t rolling_buffer_get_incoming_power(const struct rolling_buffer_t *b)
+{
+    return (power_t)((uint64_t)b->incoming_power << (BUFFER_SIZE_BITS - 1)) - b->incoming_total * b->incoming_total;
+}
+extern "C" power_t rolling_buffer_get_outgoing_power(const struct rolling_buffer_t *b)
+{
+    return (power_t)((uint64_t)b->outgoing_power << (BUFFER_SIZE_BITS - 1)) - b->outgoing_total * b->outgoing_total;
+}
+
+extern "C" void rolling_buffer_write_out(const struct rolling_buffer_t *rb, struct buffer_t *dst)
+{
+    at_context *c = default_ctx();
+    int16_t *d_in = (int16_t *)c->d_scratch, *d_out = d_in + BUFFER_SIZE;
+    long long *d_pow = (long long *)(d_out + BUFFER_SIZE);
+    CUX(cudaMemcpyAsync(d_in, rb->buffer, sizeof rb->buffer, cudaMemcpyHostToDevice, c->stream), "rolling_buffer_write_out");
+    CUX(at_launch_write_out(d_in, rb->head & (BUFFER_SIZE - 1), BUFFER_SIZE_BITS, d_out, d_pow, c->stream), "rolling_buffer_write_out");
+    CUX(cudaMemcpyAsync(dst->buffer, d_out, sizeof dst->buffer, cudaMemcpyDeviceToHost, c->stream), "rolling_buffer_write_out");
+    CUX(cudaMemcpyAsync(&dst->power, d_pow, sizeof dst->power, cudaMemcpyDeviceToHost, c->stream), "rolling_buffer_write_out");
+    CUX(cudaStreamSynchronize(c->stream), "rolling_buffer_write_out");
+}
+
+extern "C" void buffer_normalize_range(struct buffer_t *buf)
+{
+    at_context *c = default_ctx();
+    int16_t *d = (int16_t *)c->d_scratch;
+    CUX(cudaMemcpyAsync(d, buf->buffer, sizeof buf->buffer, cudaMemcpyHostToDevice, c->stream), "buffer_normalize_range");
+    CUX(at_launch_shift8(d, BUFFER_SIZE, c->stream), "buffer_normalize_range");
+    CUX(cudaMemcpyAsync(buf->buffer, d, sizeof buf->buffer, cudaMemcpyDeviceToHost, c->stream), "buffer_normalize_range");
+    CUX(cudaStreamSynchronize(c->stream), "buffer_normalize_range");
+}
+
+extern "C" void buffer_window(struct buffer_t *buf)
+{
+    at_context *c = default_ctx();
+    int16_t *d = (int16_t *)c->d_scratch;
+    CUX(cudaMemcpyAsync(d, buf->buffer, sizeof buf->buffer, cudaMemcpyHostToDevice, c->stream), "buffer_window");
+    CUX(at_launch_window(d, BUFFER_SIZE, c->d_window, c->stream), "buffer_window");
+    CUX(cudaMemcpyAsync(buf->buffer, d, sizeof buf->buffer, cudaMemcpyDeviceToHost, c->stream), "buffer_window");
+    CUX(cudaStreamSynchronize(c->stream), "buffer_window");
+}
+
+extern "C" void correlations_init(struct correlations_t *corr, const struct buffer_t *a, const struct buffer_t *b)
+{
+    default_ctx();
+    at_context *c = g_pair;
+    int16_t *d_sig = (int16_t *)c->d_scratch;
+    struct correlations_t *d_corr = (struct correlations_t *)(d_sig + 2 * BUFFER_SIZE);
+    CUX(cudaMemcpyAsync(d_sig, a->buffer, sizeof a->buffer, cudaMemcpyHostToDevice, c->stream), "correlations_init");
+    CUX(cudaMemcpyAsync(d_sig + BUFFER_SIZE, b->buffer, sizeof b->buffer, cudaMemcpyHostToDevice, c->stream), "correlations_init");
+    AtFusedParams p;
+    memset(&p, 0, sizeof p);
+    p.sig16 = d_sig; p.n_frames = 1; p.corr = d_corr; p.corr_struct = 1; p.now_us = at_get_time_us();
+    const AtShape sh = {2, BUFFER_SIZE_BITS, MAX_SHIFT_SAMPLES};
+    if (launch_fused(c, sh, p, AT_KERNEL_IMAD, c->stream) != AT_OK) die("correlations_init");
+    CUX(cudaMemcpyAsync(corr, d_corr, sizeof *corr, cudaMemcpyDeviceToHost, c->stream), "correlations_init");
+    CUX(cudaStreamSynchronize(c->stream), "correlations_init");
+}
+
+extern "C" void correlations_average(struct correlations_t *est, struct correlations_t *fresh)
+{
+    at_context *c = default_ctx();
+    const uint64_t now = at_get_time_us();
+    // decay with the host libm so the float matches the reference build bit for bit (correlations.c:42-43)
+    const float dt = (float)(now - est->last_update) / 1e6f;
+    const float decay = (float)(1.0 - exp((double)(-dt / 0.5f)));
+    char *base = (char *)c->d_scratch;
+    long long *d_est = (long long *)base, *d_new = d_est + CORRELATION_BUFFER_SIZE;
+    unsigned long long *d_time = (unsigned long long *)(d_new + CORRELATION_BUFFER_SIZE);
+    int32_t *d_best = (int32_t *)(d_time + 1);
+    float *d_decay = (float *)(d_best + 2);
+    CUX(cudaMemcpyAsync(d_est, est->correlations, sizeof est->correlations, cudaMemcpyHostToDevice, c->stream), "correlations_average");
+    CUX(cudaMemcpyAsync(d_new, fresh->correlations, sizeof fresh->correlations, cudaMemcpyHostToDevice, c->stream), "correlations_average");
+    CUX(cudaMemcpyAsync(d_time, &est->last_update, 8, cudaMemcpyHostToDevice, c->stream), "correlations_average");
+    CUX(cudaMemcpyAsync(d_decay, &decay, 4, cudaMemcpyHostToDevice, c->stream), "correlations_average");
+    CUX(at_launch_average(d_est, d_best, d_time, d_new, nullptr, 1, 1, MAX_SHIFT_SAMPLES, now, d_decay, c->stream), "correlations_average");
+    CUX(cudaMemcpyAsync(est->correlations, d_est, sizeof est->correlations, cudaMemcpyDeviceToHost, c->stream), "correlations_average");
+    CUX(cudaMemcpyAsync(&est->best_shift, d_best, 4, cudaMemcpyDeviceToHost, c->stream), "correlations_average");
+    CUX(cudaStreamSynchronize(c->stream), "correlations_average");
+    est->last_update = now;
+}

@@ -1,0 +1,69 @@
+// at_internal.h -- declarations shared by the CUDA translation units of libat_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#define AT_MAX_MICS_I 8
+#define AT_MAX_PAIRS (AT_MAX_MICS_I * (AT_MAX_MICS_I - 1) / 2)
+
+// Everything one launch of the fused localization kernel needs.  Device pointers.
+struct AtFusedParams {
+    // inputs
+    const uint8_t *adc;      // [F][M][N] ring order (or NULL when sig16 is used)
+    const int16_t *sig16;    // [F][M][N] already prepared frames (drop-in correlations_init path)
+    const int32_t *heads;    // [F] or NULL
+    unsigned long long n_frames;
+    // outputs (any may be NULL)
+    int32_t *lags;
+    void *corr; int32_t corr_struct;
+    long long *raw;
+    int32_t *cell; long long *highest; float *xy;
+    uint8_t *gate; uint8_t *classes;
+    int16_t *windowed; long long *power;
+    // tables
+    const int16_t *window;   // [N] Q15, already decimated to the frame length
+    const float *gauss;      // [2L+1]: exp(-d*d/36) for d = 0..2L, computed with the host libm
+    const uint8_t *lut;      // [P][cells]
+    const uint8_t *cand_idx; // [P][n_cand] distinct lag-index tuples of the LUT
+    const int32_t *cand_cell;// [n_cand] first row-major cell of each tuple, ascending
+    int32_t n_cand, n_cells, half_w, half_h;
+    float px_per_m;
+    unsigned long long now_us;
+};
+
+struct AtShape { int n_mics, n_bits, max_shift; };
+
+// at_fused_imad.cu -- returns cudaErrorInvalidValue for a shape with no instantiation
+cudaError_t at_launch_fused_imad(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
+// at_fused_imma.cu
+cudaError_t at_launch_fused_imma(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
+bool at_fused_imma_supports(const AtShape &shape);
+
+// at_aux.cu -- small kernels
+cudaError_t at_launch_mics_triangle(float d_ab, float d_bc, float d_ca, int mirror, float *d_xy, cudaStream_t st);
+cudaError_t at_launch_lut_build(const float *d_mic_xy, int n_mics, int L, float rate_hz, float speed,
+                                int half_w, int half_h, float px_per_m, float height, uint8_t *d_lut,
+                                cudaStream_t st);
+cudaError_t at_launch_write_out(const int16_t *d_ring, int head, int n_bits, int16_t *d_out, long long *d_power,
+                                cudaStream_t st);
+cudaError_t at_launch_shift8(int16_t *d_x, int n, cudaStream_t st);
+cudaError_t at_launch_window(int16_t *d_x, int n, const int16_t *d_window, cudaStream_t st);
+cudaError_t at_launch_average(long long *d_est, int32_t *d_est_best, unsigned long long *d_est_time,
+                              const long long *d_fresh, const uint8_t *d_gate, size_t n_arrays, int n_pairs,
+                              int L, unsigned long long now_us, const float *d_decay /*NULL: compute*/,
+                              cudaStream_t st);
+cudaError_t at_launch_heatmap(const long long *d_corr, size_t n_arrays, int n_pairs, int L,
+                              const uint8_t *d_lut, const uint8_t *d_cand_idx, const int32_t *d_cand_cell,
+                              int n_cand, int n_cells, int half_w, int half_h, float px_per_m,
+                              int32_t *d_cell, long long *d_highest, float *d_xy, uint8_t *d_classes,
+                              cudaStream_t st);
+cudaError_t at_launch_synth(unsigned long long seed, unsigned flags, size_t first, size_t n_frames, int n_mics,
+                            int n_bits, int n_cells, const int32_t *d_delay_q8, uint8_t *d_adc, int32_t *d_heads,
+                            int32_t *d_cell, cudaStream_t st);
+cudaError_t at_launch_stream_push(int n_mics, int n_bits, size_t n_arrays, size_t n_ticks, const uint8_t *d_samples,
+                                  int16_t *d_ring, long long *d_sums, int32_t *d_head_full, int32_t *d_fired,
+                                  uint8_t *d_frames, int32_t *d_heads, cudaStream_t st);
+cudaError_t at_run_microbench(int which, int sm_count, double *gops, double *mhz, cudaStream_t st);
+
+void at_count_launch(unsigned n = 1);
