@@ -303,7 +303,7 @@ extern "C" int at_localize_device(at_context *c, const uint8_t *d_adc, const int
     p.gate = o->gate; p.classes = o->classes; p.windowed = o->windowed; p.power = (long long *)o->power;
     p.now_us = at_get_time_us();
     const AtShape sh = {c->cfg.n_mics, c->cfg.n_bits, c->cfg.max_shift};
-    return launch_fused(c, sh, p, c->cfg.kernel, stream ? (cudaStream_t)stream : c->stream);
+    return launch_fused(c, sh, p, c->cfg.kernel, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ fused path, host API
@@ -427,7 +427,7 @@ extern "C" int at_average_device(at_context *c, int64_t *d_est, int32_t *d_est_b
     CU(cudaSetDevice(c->cfg.device));
     CU(at_launch_average((long long *)d_est, d_est_best, (unsigned long long *)d_est_time, (const long long *)d_fresh,
                          d_gate, n_arrays, c->n_pairs, c->cfg.max_shift, now_us, nullptr,
-                         stream ? (cudaStream_t)stream : c->stream));
+                         (cudaStream_t)stream));
     return AT_OK;
 }
 
@@ -438,7 +438,7 @@ extern "C" int at_heatmap_device(at_context *c, const int64_t *d_corr, size_t n_
     CU(cudaSetDevice(c->cfg.device));
     CU(at_launch_heatmap((const long long *)d_corr, n_arrays, c->n_pairs, c->cfg.max_shift, c->d_lut, c->d_cand_idx,
                          c->d_cand_cell, c->n_cand, c->n_cells, c->cfg.half_w, c->cfg.half_h, c->cfg.px_per_m, d_cell,
-                         (long long *)d_highest, d_xy, d_classes, stream ? (cudaStream_t)stream : c->stream));
+                         (long long *)d_highest, d_xy, d_classes, (cudaStream_t)stream));
     return AT_OK;
 }
 
@@ -469,7 +469,7 @@ extern "C" int at_synth_device(at_context *c, uint64_t seed, uint32_t flags, siz
     if (!c || !d_adc) return fail(AT_EINVAL, "at_synth_device: null argument");
     CU(cudaSetDevice(c->cfg.device));
     CU(at_launch_synth(seed, flags, first, n_frames, c->cfg.n_mics, c->cfg.n_bits, c->n_cells, c->d_delay_q8, d_adc,
-                       d_heads, d_true_cell, stream ? (cudaStream_t)stream : c->stream));
+                       d_heads, d_true_cell, (cudaStream_t)stream));
     return AT_OK;
 }
 

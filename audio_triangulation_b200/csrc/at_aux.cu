@@ -216,51 +216,39 @@ __global__ void synth_kernel(unsigned long long seed, unsigned flags, unsigned l
 }
 
 // ------------------------------------------------------------------ pipe-rate microbenchmarks
+// Every instruction takes an operand produced by the previous iteration (a different accumulator),
+// so ptxas can neither hoist the product nor fold the chain; 8 independent chains per thread.
 template <int WHICH>
 __global__ void __launch_bounds__(256) ubench_kernel(int iters, int seed, long long *sink, long long *cycles)
 {
     const int tid = threadIdx.x;
     long long t0 = clock64();
-    if (WHICH == 0) {          // IMAD.WIDE : 8 independent 64-bit accumulators
+    if (WHICH == 0) {          // mad.wide.s32 (int32 x int32 + int64)
         long long a[8];
-        int x = seed + tid, y = seed * 3 + 1;
-        for (int j = 0; j < 8; j++) a[j] = j;
+        const int y = seed * 3 + 1;
+        for (int j = 0; j < 8; j++) a[j] = j + tid;
         for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(a[j]) : "r"(x), "r"(y));
+            for (int j = 0; j < 8; j++) {
+                const int x = (int)a[(j + 1) & 7];
+                asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(a[j]) : "r"(x), "r"(y));
+            }
         }
         long long s = 0;
         for (int j = 0; j < 8; j++) s += a[j];
         if (s == 0x1234567) sink[0] = s;
-    } else if (WHICH == 1) {   // IMAD 32-bit
+    } else if (WHICH == 1 || WHICH == 2 || WHICH == 3) {   // mad.lo.s32 / dp2a / dp4a
         int a[8];
-        int x = seed + tid, y = seed * 3 + 1;
-        for (int j = 0; j < 8; j++) a[j] = j;
+        const int y = seed * 3 + 1;
+        for (int j = 0; j < 8; j++) a[j] = j + tid;
         for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(a[j]) : "r"(x), "r"(y));
-        }
-        int s = 0;
-        for (int j = 0; j < 8; j++) s += a[j];
-        if (s == 0x1234567) sink[0] = s;
-    } else if (WHICH == 2) {   // IDP.2A
-        int a[8];
-        int x = seed + tid, y = seed * 3 + 1;
-        for (int j = 0; j < 8; j++) a[j] = j;
-        for (int it = 0; it < iters; it++) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) asm volatile("dp2a.lo.s32.s32 %0, %1, %2, %0;" : "+r"(a[j]) : "r"(x), "r"(y));
-        }
-        int s = 0;
-        for (int j = 0; j < 8; j++) s += a[j];
-        if (s == 0x1234567) sink[0] = s;
-    } else if (WHICH == 3) {   // IDP.4A
-        int a[8];
-        int x = seed + tid, y = seed * 3 + 1;
-        for (int j = 0; j < 8; j++) a[j] = j;
-        for (int it = 0; it < iters; it++) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(a[j]) : "r"(x), "r"(y));
+            for (int j = 0; j < 8; j++) {
+                const int x = a[(j + 1) & 7];
+                if (WHICH == 1) asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(a[j]) : "r"(x), "r"(y));
+                if (WHICH == 2) asm volatile("dp2a.lo.s32.s32 %0, %1, %2, %0;" : "+r"(a[j]) : "r"(x), "r"(y));
+                if (WHICH == 3) asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(a[j]) : "r"(x), "r"(y));
+            }
         }
         int s = 0;
         for (int j = 0; j < 8; j++) s += a[j];
@@ -292,18 +280,18 @@ __global__ void __launch_bounds__(256) ubench_kernel(int iters, int seed, long l
             for (int j = 0; j < 4; j++) {
                 uint4 v;
                 const uint32_t addr = smem_u32(&buf[(tid + 256 * j) & 1023]);
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+                asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
                 acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
             }
         }
         if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x1234567) sink[0] = acc.x;
     } else {                   // DFMA
         double a[8];
-        double x = 1.0 + 1e-9 * tid, y = 1e-9 * seed;
-        for (int j = 0; j < 8; j++) a[j] = j;
+        const double y = 1e-9 * seed;
+        for (int j = 0; j < 8; j++) a[j] = j + 1e-3 * tid;
         for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) asm volatile("fma.rn.f64 %0, %1, %0, %2;" : "+d"(a[j]) : "d"(x), "d"(y));
+            for (int j = 0; j < 8; j++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a[j]) : "d"(a[(j + 1) & 7]), "d"(y));
         }
         double s = 0;
         for (int j = 0; j < 8; j++) s += a[j];
@@ -403,7 +391,7 @@ static cudaError_t run_ubench(int sm_count, double ops_per_thread_iter, double *
     long long *d = nullptr;
     cudaError_t e = cudaMalloc(&d, 2 * sizeof(long long));
     if (e != cudaSuccess) return e;
-    const int iters = 4096, blocks = sm_count * 8;
+    const int iters = 4096, blocks = sm_count * 4;   // 4 x 256 threads per SM: all blocks co-resident
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);
     ubench_kernel<WHICH><<<blocks, 256, 0, st>>>(64, 1, d, d + 1);       // warm-up
@@ -421,7 +409,7 @@ static cudaError_t run_ubench(int sm_count, double ops_per_thread_iter, double *
     if (e != cudaSuccess) return e;
     const double total = ops_per_thread_iter * iters * 256.0 * blocks;
     *gops = total / (ms * 1e-3) / 1e9;
-    // block 0 ran for cyc[1] cycles; 8 blocks per SM run concurrently for the whole launch
+    // block 0 ran for cyc[1] cycles; all blocks are co-resident, so that spans the whole launch
     if (mhz) *mhz = (double)cyc[1] / (ms * 1e-3) / 1e6;
     return cudaGetLastError();
 }

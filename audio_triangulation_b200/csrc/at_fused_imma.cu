@@ -1,11 +1,355 @@
 // at_fused_imma.cu -- fused localization kernel, int8 tensor-core form (AT_KERNEL_IMMA).
-// Placeholder until the byte-split Toeplitz x Hankel kernel lands: no shape is supported, so
-// AT_KERNEL_AUTO resolves to the integer-pipe kernel.
-#include "at_internal.h"
+//
+// The lagged cross-correlation of one microphone pair (ref: components/correlations.c:9-18),
+//     corr[s] = sum_i x[i] * y[i+s],   s in [-L, L],
+// is a Toeplitz x Hankel matrix product once the lag index j = s + PAD is split as j = 8 r + n:
+//     D[r][n] = sum_p  A[r][p] * B[p][n],   A[r][p] = y~[p + 8 r - PAD]  (Hankel, row stride 8)
+//                                           B[p][n] = x~[p - n]          (Toeplitz)
+// with x~, y~ the zero-extended frames and p running over N + 8 samples.  That is exactly one
+// mma.sync m16n8k32 tile (16 x 8 = 128 lags, 93 used) per 32 samples.  int16 operands are split
+// into a signed high byte and an unsigned low byte, w = 256 h + l, giving four int8 products
+//     corr = 65536 * (h.h) + 256 * (h.l + l.h) + (l.l)
+// whose int32 accumulators cannot overflow over a frame (|h.h| <= 2^24, |h.l + l.h| < 2^26,
+// l.l < 2^26 at N = 1024; 4x that at N = 4096), recombined in int64: bit-identical to the
+// reference's int64 accumulation.
+//
+// Mapping: ONE WARP PER FRAME.  A warp loads its frame (coalesced 16-byte global loads), removes
+// DC, applies <<8 and the window, writes hi/lo byte planes of the three channels to its private
+// shared-memory slice, runs 33 k-steps x 12 IMMA (3 pairs x {hh, hl, lh, ll}) with fragments
+// loaded straight from the planes (A: aligned 8-byte loads, the Hankel rows overlap in memory;
+// B: aligned 4-byte loads + funnel shift for the per-column byte offset), then finds the three
+// arg-max lags with warp shuffles.  No block-level synchronisation after start-up.
+#include <limits.h>
 
-bool at_fused_imma_supports(const AtShape &) { return false; }
+#include "at_fused_common.cuh"
 
-cudaError_t at_launch_fused_imma(const AtShape &, const AtFusedParams &, int, cudaStream_t)
+namespace atk {
+
+template <int NBITS, int L>
+struct ImmaGeo {
+    static constexpr int N = 1 << NBITS;
+    static constexpr int PAD = round_up(L, 16);                 // lag index j = s + PAD; 48 for L = 46 / 44
+    static constexpr int KSTEPS = ceil_div(N + 8, 32);          // 33: p runs over [0, N + 8)
+    static constexpr int PLANE = round_up(32 * KSTEPS + 8 * 15 + 8, 16);   // bytes per byte-plane: 1184
+    static constexpr int NJ = 96;                               // lag slots kept in the epilogue scratch (rows 0..11)
+    static constexpr int NL = 2 * L + 1;
+    static_assert(PAD + L < NJ, "lag range does not fit rows 0..11 of the 16 x 8 tile");
+};
+
+template <int NBITS, int L, int WARPS>
+struct ImmaSmem {
+    using G = ImmaGeo<NBITS, L>;
+    alignas(16) uint16_t win2[G::N];                 // 2 * W[i]: (a * 2W) >> 8 == (a * W) >> 7, byte aligned
+    float gauss[2 * L + 1];
+    alignas(16) uint8_t plane[WARPS][3][2][G::PLANE]; // [warp][channel][hi, lo]
+    alignas(8) long long curve[WARPS][3][G::NJ];      // epilogue scratch
+    int best[WARPS][4];
+};
+
+// D += A * B, m16n8k32, int8 operands with per-operand signedness, int32 accumulate
+#define AT_MMA(TA, TB)                                                                                          \
+    __device__ __forceinline__ void mma_##TA##_##TB(int (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])  \
+    {                                                                                                           \
+        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32." #TA "." #TB ".s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, " \
+                     "{%8,%9}, {%0,%1,%2,%3};"                                                                  \
+                     : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])                                           \
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));                       \
+    }
+AT_MMA(s8, s8)
+AT_MMA(s8, u8)
+AT_MMA(u8, s8)
+AT_MMA(u8, u8)
+#undef AT_MMA
+
+__device__ __forceinline__ uint4 ldg_stream(const uint8_t *p)
 {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Sign-extend one byte of a word with a single PRMT (selector nibble 8+e = "replicate the sign of
+// byte e").  Raw PTX: __byte_perm() is specified to ignore bit 3 of each nibble and nvcc masks it.
+template <int SEL>
+__device__ __forceinline__ int sext_byte(uint32_t w)
+{
+    int r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "n"(SEL));
+    return r;
+}
+
+// A fragment (16 x 32, rows = Hankel rows of y): two aligned 8-byte loads
+__device__ __forceinline__ void load_a(uint32_t (&a)[4], const uint8_t *plane_k0_aoff)
+{
+    const uint2 lo = *reinterpret_cast<const uint2 *>(plane_k0_aoff);        // row g   : k = 8t .. 8t+7
+    const uint2 hi = *reinterpret_cast<const uint2 *>(plane_k0_aoff + 64);   // row g+8
+    a[0] = lo.x; a[2] = lo.y; a[1] = hi.x; a[3] = hi.y;
+}
+// B fragment (32 x 8, column n = x shifted by n bytes): three aligned words + funnel shift
+__device__ __forceinline__ void load_b(uint32_t (&b)[2], const uint8_t *plane_k0_bal, int bsh)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(plane_k0_bal);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    b[0] = __funnelshift_r(w0, w1, bsh);
+    b[1] = __funnelshift_r(w1, w2, bsh);
+}
+
+// Warp-scope epilogue for the optional products; curve[][] holds raw sums indexed by j = s + PAD.
+template <int L, int PAD, int NJ>
+__device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], const int *best, const float *gauss_s,
+                                              const AtFusedParams &p, unsigned long long f, int lane)
+{
+    constexpr int P = 3, NL = 2 * L + 1, OFF = PAD - L;
+    if (p.gate && lane == 0) {                                   // sample_compute.h:124-134
+        const int tot = best[0] * best[0] + best[1] * best[1] + best[2] * best[2];
+        p.gate[f] = tot > 4 ? 1 : 0;
+    }
+    if (p.raw)
+        for (int idx = lane; idx < P * NL; idx += 32) p.raw[f * (unsigned long long)(P * NL) + idx] = curve[idx / NL][OFF + idx % NL];
+    if (!(p.corr || p.cell || p.highest || p.xy || p.classes)) return;
+    __syncwarp();
+    for (int idx = lane; idx < P * NL; idx += 32) {              // correlations.c:26-33
+        const int pr = idx / NL, li = idx % NL;
+        int d = (li - L) - best[pr];
+        d = d < 0 ? -d : d;
+        curve[pr][OFF + li] = __float2ll_rz(__fmul_rn(__ll2float_rn(curve[pr][OFF + li]), gauss_s[d]));
+    }
+    __syncwarp();
+    if (p.corr) {
+        if (p.corr_struct) {
+            long long *base = reinterpret_cast<long long *>(p.corr) + f * (unsigned long long)(P * (NL + 2));
+            for (int idx = lane; idx < P * (NL + 2); idx += 32) {
+                const int pr = idx / (NL + 2), k = idx % (NL + 2);
+                base[idx] = k < NL ? curve[pr][OFF + k] : (k == NL ? (long long)(unsigned)best[pr] : (long long)p.now_us);
+            }
+        } else {
+            long long *base = reinterpret_cast<long long *>(p.corr) + f * (unsigned long long)(P * NL);
+            for (int idx = lane; idx < P * NL; idx += 32) base[idx] = curve[idx / NL][OFF + idx % NL];
+        }
+    }
+    if (!(p.cell || p.highest || p.xy || p.classes)) return;
+    Best b = {LLONG_MIN, 0x7fffffff};                            // vga_heatmap.h:96-108 over distinct tuples
+    for (int c = lane; c < p.n_cand; c += 32) {
+        long long like = 0;
+#pragma unroll
+        for (int pr = 0; pr < P; pr++) like += curve[pr][OFF + p.cand_idx[pr * p.n_cand + c]];
+        if (like > b.v) { b.v = like; b.i = c; }
+    }
+    b = warp_best(b);
+    if (lane == 0) {
+        const int cellidx = p.cand_cell[b.i];
+        if (p.cell) p.cell[f] = cellidx;
+        if (p.highest) p.highest[f] = b.v;
+        if (p.xy) {
+            const int W = 2 * p.half_w + 1;
+            p.xy[2 * f + 0] = __fdiv_rn((float)(cellidx % W - p.half_w), p.px_per_m);
+            p.xy[2 * f + 1] = __fdiv_rn((float)(p.half_h - cellidx / W), p.px_per_m);
+        }
+    }
+    if (p.classes) {                                             // vga_heatmap.h:111-126
+        const long long top = b.v;
+        const long long tw = (top * 63) >> 6, tg = (top * 31) >> 5, tr = (top * 15) >> 4, tb = (top * 7) >> 3;
+        for (int c = lane; c < p.n_cells; c += 32) {
+            long long like = 0;
+#pragma unroll
+            for (int pr = 0; pr < P; pr++) like += curve[pr][OFF + p.lut[pr * p.n_cells + c]];
+            p.classes[f * (unsigned long long)p.n_cells + c] = like >= tw ? 15 : like >= tg ? 3 : like >= tr ? 8 : like >= tb ? 5 : 0;
+        }
+    }
+}
+
+template <int NBITS, int L, int WARPS, int CTAS_PER_SM>
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(const AtFusedParams p)
+{
+    using G = ImmaGeo<NBITS, L>;
+    using S = ImmaSmem<NBITS, L, WARPS>;
+    constexpr int N = G::N, PAD = G::PAD, PLANE = G::PLANE;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    S &s = *reinterpret_cast<S *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    // one-time CTA setup: zero every plane (the pads stay zero), doubled window, Gaussian factors
+    for (int i = tid; i < (int)(sizeof(s.plane) / 16); i += WARPS * 32)
+        reinterpret_cast<uint4 *>(&s.plane[0][0][0][0])[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < N; i += WARPS * 32) s.win2[i] = (uint16_t)(2 * (int)p.window[i]);
+    for (int i = tid; i < 2 * L + 1; i += WARPS * 32) s.gauss[i] = p.gauss[i];
+    __syncthreads();
+
+    uint8_t *const pl = &s.plane[warp][0][0][0];
+    auto plane = [&](int ch, int hl) -> uint8_t * { return pl + (ch * 2 + hl) * PLANE; };
+    const int aoff = 8 * t + 8 * g;                 // A: plane index of (row g, k = 8t) at k0 = 0
+    const int boff = 8 * t - g + PAD;               // B: plane index of (k = 8t, column g)
+    const int bal = boff & ~3, bsh = (boff & 3) * 8;
+    const bool extras = p.gate || p.raw || p.corr || p.cell || p.highest || p.xy || p.classes;
+
+    const unsigned long long stride = (unsigned long long)gridDim.x * WARPS;
+    for (unsigned long long f = (unsigned long long)blockIdx.x * WARPS + warp; f < p.n_frames; f += stride) {
+        const uint8_t *src = p.adc + f * (unsigned long long)(3 * N);
+        const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
+
+        // ---- channel sums -> floor mean (rolling_buffer.c:48-64); the sum is rotation invariant
+        constexpr int Q = N / 512;               // 16-byte loads per lane and channel
+        constexpr bool KEEP = Q <= 2;            // N = 1024: the whole frame stays in 24 registers
+        uint4 raw[KEEP ? 3 * Q : 1];
+        int mean[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            unsigned sum = 0;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const uint4 v = KEEP ? ldg_stream(src + ch * N + q * 512 + lane * 16)
+                                     : __ldg(reinterpret_cast<const uint4 *>(src + ch * N + q * 512 + lane * 16));
+                if (KEEP) raw[ch * Q + q] = v;
+                sum = __dp4a(v.x, 0x01010101u, sum); sum = __dp4a(v.y, 0x01010101u, sum);
+                sum = __dp4a(v.z, 0x01010101u, sum); sum = __dp4a(v.w, 0x01010101u, sum);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            mean[ch] = (int)(sum >> NBITS);
+        }
+
+        // ---- DC removal, <<8, window -> hi / lo byte planes (rolling_buffer.c:66, buffer.c:16, :8-9)
+        //      (int16)((b - mean) << 8) = 256 * sext8(b - mean);  ((256 a) * W) >> 15 = (a * 2W) >> 8
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const uint32_t m4 = (uint32_t)(mean[ch] & 0xFF) * 0x01010101u;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const int j0 = q * 512 + lane * 16;                   // ring slot of this lane's 16 bytes
+                const uint4 v = KEEP ? raw[ch * Q + q] : __ldg(reinterpret_cast<const uint4 *>(src + ch * N + j0));
+                const uint32_t rw[4] = {v.x, v.y, v.z, v.w};
+                if ((head & 15) == 0) {
+                    const int i0 = (j0 - head) & (N - 1);             // chronological index, 16-aligned
+                    const uint4 wa = *reinterpret_cast<const uint4 *>(&s.win2[i0]);
+                    const uint4 wb = *reinterpret_cast<const uint4 *>(&s.win2[i0 + 8]);
+                    const uint32_t ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; w4++) {
+                        const uint32_t d = __vsub4(rw[w4], m4);      // (b - mean) mod 256, per byte
+                        const int a0 = sext_byte<0x8880>(d), a1 = sext_byte<0x9991>(d);
+                        const int a2 = sext_byte<0xaaa2>(d), a3 = sext_byte<0xbbb3>(d);
+                        const int p0 = a0 * (int)(ww[2 * w4] & 0xFFFFu), p1 = a1 * (int)(ww[2 * w4] >> 16);
+                        const int p2 = a2 * (int)(ww[2 * w4 + 1] & 0xFFFFu), p3 = a3 * (int)(ww[2 * w4 + 1] >> 16);
+                        // prepared sample = bits 8..23 of the product: low byte = byte 1, high byte = byte 2
+                        const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
+                        const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
+                        lo[w4] = __byte_perm(t01, t23, 0x5410);
+                        hi[w4] = __byte_perm(t01, t23, 0x7632);
+                    }
+                    *reinterpret_cast<uint4 *>(plane(ch, 0) + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(plane(ch, 1) + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                } else {   // ring head not 16-aligned: scalar stores (rare; capture heads are arbitrary)
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const int i = (j0 + e - head) & (N - 1);
+                        const int a = (int)(signed char)(((rw[e >> 2] >> (8 * (e & 3))) - (uint32_t)mean[ch]) & 0xFFu);
+                        const int pr = a * (int)s.win2[i];
+                        plane(ch, 0)[PAD + i] = (uint8_t)(pr >> 16);
+                        plane(ch, 1)[PAD + i] = (uint8_t)(pr >> 8);
+                    }
+                }
+            }
+            if (p.power) {   // rolling_buffer.c:68-70: power of the DC-removed samples (9-bit differences)
+                long long acc = 0;
+                for (int k = lane; k < N; k += 32) { const int dv = (int)src[ch * N + k] - mean[ch]; acc += (long long)dv * dv; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) p.power[f * 3 + ch] = acc;
+            }
+        }
+        __syncwarp();
+        if (p.windowed)
+            for (int idx = lane; idx < 3 * N; idx += 32) {
+                const int ch = idx / N, i = idx % N;
+                p.windowed[f * (unsigned long long)(3 * N) + idx] =
+                    (int16_t)(((int)(signed char)plane(ch, 0)[PAD + i] << 8) | plane(ch, 1)[PAD + i]);
+            }
+
+        // ---- 33 k-steps x 12 IMMA: pairs (a,b), (a,c), (b,c); x = first, y = second mic
+        int acc[3][3][4];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[a][b][c] = 0;
+        const uint8_t *ya = pl + aoff, *xb = pl + bal;   // + (ch*2+hl)*PLANE + k0
+#pragma unroll 3
+        for (int ks = 0; ks < G::KSTEPS; ks++) {
+            const int k0 = 32 * ks;
+            uint32_t Ybh[4], Ybl[4], Ych[4], Ycl[4], Xah[2], Xal[2], Xbh[2], Xbl[2];
+            load_a(Ybh, ya + 2 * PLANE + k0); load_a(Ybl, ya + 3 * PLANE + k0);
+            load_a(Ych, ya + 4 * PLANE + k0); load_a(Ycl, ya + 5 * PLANE + k0);
+            load_b(Xah, xb + 0 * PLANE + k0, bsh); load_b(Xal, xb + 1 * PLANE + k0, bsh);
+            load_b(Xbh, xb + 2 * PLANE + k0, bsh); load_b(Xbl, xb + 3 * PLANE + k0, bsh);
+            mma_s8_s8(acc[0][0], Ybh, Xah); mma_s8_u8(acc[0][1], Ybh, Xal); mma_u8_u8(acc[0][2], Ybl, Xal);
+            mma_s8_s8(acc[1][0], Ych, Xah); mma_s8_u8(acc[1][1], Ych, Xal); mma_u8_u8(acc[1][2], Ycl, Xal);
+            mma_s8_s8(acc[2][0], Ych, Xbh); mma_s8_u8(acc[2][1], Ych, Xbl); mma_u8_u8(acc[2][2], Ycl, Xbl);
+            mma_u8_s8(acc[0][1], Ybl, Xah); mma_u8_s8(acc[1][1], Ycl, Xah); mma_u8_s8(acc[2][1], Ycl, Xbh);
+        }
+
+        // ---- recombine in int64, arg-max per pair (correlations.c:20-23)
+        int best3[3];
+#pragma unroll
+        for (int pr = 0; pr < 3; pr++) {
+            Best b = {LLONG_MIN, 0x7fffffff};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
+                const long long v = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i] + (long long)acc[pr][2][i];
+                if (extras && j < G::NJ) s.curve[warp][pr][j] = v;
+                if (j >= PAD - L && j <= PAD + L && v > b.v) { b.v = v; b.i = j; }
+            }
+            b = warp_best(b);
+            best3[pr] = b.i - PAD;
+        }
+        if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? best3[0] : (lane == 1 ? best3[1] : best3[2]);
+        if (extras) {
+            if (lane == 0) { s.best[warp][0] = best3[0]; s.best[warp][1] = best3[1]; s.best[warp][2] = best3[2]; }
+            __syncwarp();
+            epilogue_warp<L, PAD, G::NJ>(s.curve[warp], s.best[warp], s.gauss, p, f, lane);
+        }
+        __syncwarp();   // planes and scratch are rewritten by the next frame
+    }
+}
+
+template <int NBITS, int L, int WARPS, int CTAS_PER_SM>
+static cudaError_t launch_imma(const AtFusedParams &p, int sm_count, cudaStream_t st)
+{
+    using S = ImmaSmem<NBITS, L, WARPS>;
+    auto kern = at_fused_imma_kernel<NBITS, L, WARPS, CTAS_PER_SM>;
+    const int smem = (int)sizeof(S);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    unsigned long long grid = (unsigned long long)sm_count * per_sm;
+    const unsigned long long need = (p.n_frames + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    if (grid == 0) return cudaSuccess;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(p);
+    at_count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace atk
+
+bool at_fused_imma_supports(const AtShape &sh)
+{
+    return sh.n_mics == 3 && ((sh.n_bits == 10 && (sh.max_shift == 46 || sh.max_shift == 44)) ||
+                              (sh.n_bits == 12 && sh.max_shift == 46));
+}
+
+cudaError_t at_launch_fused_imma(const AtShape &sh, const AtFusedParams &p, int sm_count, cudaStream_t st)
+{
+    if (p.sig16 || sh.n_mics != 3) return cudaErrorInvalidValue;
+    if (sh.n_bits == 10 && sh.max_shift == 46) return atk::launch_imma<10, 46, 4, 4>(p, sm_count, st);
+    if (sh.n_bits == 10 && sh.max_shift == 44) return atk::launch_imma<10, 44, 4, 4>(p, sm_count, st);
+    if (sh.n_bits == 12 && sh.max_shift == 46) return atk::launch_imma<12, 46, 4, 1>(p, sm_count, st);
     return cudaErrorInvalidValue;
 }

@@ -15,7 +15,7 @@
  *     negative AT_E* code; at_last_error() gives the text.
  *
  * Plain C, plain pointers and sizes; no CUDA/torch types in any signature (streams are passed
- * as void* holding a cudaStream_t, NULL = the context's own stream).
+ * as void* holding a cudaStream_t; NULL is CUDA's legacy default stream, as in the runtime API).
  * Citations "ref:" are relative to the reference repository's src/ directory.
  */
 #ifndef AT_B200_H
