@@ -31,7 +31,7 @@ class AtOutputs(C.Structure):
     _fields_ = [("lags", C.c_void_p), ("corr", C.c_void_p), ("corr_layout", C.c_int32),
                 ("raw", C.c_void_p), ("cell", C.c_void_p), ("highest", C.c_void_p),
                 ("xy", C.c_void_p), ("gate", C.c_void_p), ("classes", C.c_void_p),
-                ("windowed", C.c_void_p), ("power", C.c_void_p)]
+                ("windowed", C.c_void_p), ("power", C.c_void_p), ("stats", C.c_void_p)]
 
 
 class AtError(RuntimeError):

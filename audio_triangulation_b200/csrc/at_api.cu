@@ -9,6 +9,7 @@
 #include <string.h>
 #include <time.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <unordered_map>
@@ -73,6 +74,7 @@ struct at_context {
     cudaStream_t stream = nullptr;
     // device tables
     float *d_mic_xy = nullptr; uint8_t *d_lut = nullptr; uint8_t *d_cand_idx = nullptr; int32_t *d_cand_cell = nullptr;
+    uint8_t *d_cs_idx = nullptr; int32_t *d_cs_cell = nullptr; int32_t *d_cs_grid = nullptr;
     int16_t *d_window = nullptr; float *d_gauss = nullptr; int32_t *d_delay_q8 = nullptr;
     // host copies
     std::vector<float> h_mic_xy; std::vector<uint8_t> h_lut; std::vector<int32_t> h_delay_q8;
@@ -120,7 +122,8 @@ extern "C" void at_destroy(at_context *c)
         for (void *p : ptrs) if (p) cudaFree(p);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch};
+    void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
+                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -183,6 +186,28 @@ static int create_impl(const at_config *cfg, at_context *c)
         CU(cudaMalloc(&c->d_cand_cell, sizeof(int32_t) * c->n_cand));
         CU(cudaMemcpy(c->d_cand_idx, idx.data(), idx.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_cand_cell, first_cell.data(), sizeof(int32_t) * c->n_cand, cudaMemcpyHostToDevice));
+        // the same tuples ordered by (index of pair 0, index of pair 1) with a 2-D offset grid, for
+        // the kernels' bounded likelihood search (index bookkeeping only)
+        const int NLg = c->n_lags, P = c->n_pairs, T = c->n_cand;
+        std::vector<int> order(T);
+        for (int t = 0; t < T; t++) order[t] = t;
+        auto gkey = [&](int t) { return (int)(uint8_t)keys[t][0] * NLg + (P > 1 ? (int)(uint8_t)keys[t][1] : 0); };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return gkey(a) < gkey(b); });
+        std::vector<uint8_t> cs_idx((size_t)P * T);
+        std::vector<int32_t> cs_cell(T), grid((size_t)NLg * NLg + 1, 0);
+        for (int k = 0; k < T; k++) {
+            const int t = order[k];
+            for (int p = 0; p < P; p++) cs_idx[(size_t)p * T + k] = (uint8_t)keys[t][p];
+            cs_cell[k] = first_cell[t];
+            grid[gkey(t) + 1]++;
+        }
+        for (size_t i = 1; i < grid.size(); i++) grid[i] += grid[i - 1];
+        CU(cudaMalloc(&c->d_cs_idx, cs_idx.size()));
+        CU(cudaMalloc(&c->d_cs_cell, sizeof(int32_t) * T));
+        CU(cudaMalloc(&c->d_cs_grid, sizeof(int32_t) * grid.size()));
+        CU(cudaMemcpy(c->d_cs_idx, cs_idx.data(), cs_idx.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_cs_cell, cs_cell.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_cs_grid, grid.data(), sizeof(int32_t) * grid.size(), cudaMemcpyHostToDevice));
     }
 
     // window table for this frame length
@@ -272,6 +297,8 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
 {
     p.window = c->d_window; p.gauss = c->d_gauss; p.lut = c->d_lut;
     p.cand_idx = c->d_cand_idx; p.cand_cell = c->d_cand_cell;
+    p.cs_idx = c->d_cs_idx; p.cs_cell = c->d_cs_cell; p.cs_grid = c->d_cs_grid;
+    p.opaque_four = 4;
     p.n_cand = c->n_cand; p.n_cells = c->n_cells; p.half_w = c->cfg.half_w; p.half_h = c->cfg.half_h;
     p.px_per_m = c->cfg.px_per_m;
     if (kernel == AT_KERNEL_AUTO) kernel = at_fused_imma_supports(sh) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;
@@ -301,6 +328,7 @@ extern "C" int at_localize_device(at_context *c, const uint8_t *d_adc, const int
     p.lags = o->lags; p.corr = o->corr; p.corr_struct = o->corr_layout == AT_CORR_STRUCT;
     p.raw = (long long *)o->raw; p.cell = o->cell; p.highest = (long long *)o->highest; p.xy = o->xy;
     p.gate = o->gate; p.classes = o->classes; p.windowed = o->windowed; p.power = (long long *)o->power;
+    p.stats = (unsigned long long *)o->stats;
     p.now_us = at_get_time_us();
     const AtShape sh = {c->cfg.n_mics, c->cfg.n_bits, c->cfg.max_shift};
     return launch_fused(c, sh, p, c->cfg.kernel, (cudaStream_t)stream);

@@ -79,13 +79,6 @@ __device__ __forceinline__ int sext_byte(uint32_t w)
     return r;
 }
 
-// A fragment (16 x 32, rows = Hankel rows of y): two aligned 8-byte loads
-__device__ __forceinline__ void load_a(uint32_t (&a)[4], const uint8_t *plane_k0_aoff)
-{
-    const uint2 lo = *reinterpret_cast<const uint2 *>(plane_k0_aoff);        // row g   : k = 8t .. 8t+7
-    const uint2 hi = *reinterpret_cast<const uint2 *>(plane_k0_aoff + 64);   // row g+8
-    a[0] = lo.x; a[2] = lo.y; a[1] = hi.x; a[3] = hi.y;
-}
 // B fragment (32 x 8, column n = x shifted by n bytes): three aligned words + funnel shift
 __device__ __forceinline__ void load_b(uint32_t (&b)[2], const uint8_t *plane_k0_bal, int bsh)
 {
@@ -129,16 +122,70 @@ __device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], const int 
         }
     }
     if (!(p.cell || p.highest || p.xy || p.classes)) return;
-    Best b = {LLONG_MIN, 0x7fffffff};                            // vga_heatmap.h:96-108 over distinct tuples
-    for (int c = lane; c < p.n_cand; c += 32) {
-        long long like = 0;
+    // vga_heatmap.h:96-108: maximum of L = sum_pairs curve[pair][lut] over the distinct LUT tuples,
+    // first row-major cell on ties.  Exact bounded search: every entry of curve p is <= Pmax_p =
+    // max(curve[p][best_p], 0), and an entry at distance >= r from the peak is <= trunc(peak * g[r])
+    // (the re-weighting is monotone), so tuples outside a box around (best_0, best_1) cannot reach
+    // a likelihood already found inside it once  bound(r+1) + sum(other Pmax) < that likelihood.
+    Best b = {LLONG_MIN, 0x7fffffff};   // .i holds the CELL index here (lower cell wins ties)
+    {
+        const int b0 = best[0] + L, b1 = best[1] + L;
+        long long pmax[P];
+        long long others0 = 0, others1 = 0;
 #pragma unroll
-        for (int pr = 0; pr < P; pr++) like += curve[pr][OFF + p.cand_idx[pr * p.n_cand + c]];
-        if (like > b.v) { b.v = like; b.i = c; }
+        for (int pr = 0; pr < P; pr++) {
+            const long long v = curve[pr][OFF + best[pr] + L];
+            pmax[pr] = v > 0 ? v : 0;
+            if (pr != 0) others0 += pmax[pr];
+            if (pr != 1) others1 += pmax[pr];
+        }
+        const float pk0 = __ll2float_rn(pmax[0]), pk1 = __ll2float_rn(pmax[1]);   // exact: both came from floats
+        auto scan_box = [&](int r0, int r1) {
+            Best bb = {LLONG_MIN, 0x7fffffff};
+            const int w1 = 2 * r1 + 1, cells = (2 * r0 + 1) * w1;
+            for (int q = lane; q < cells; q += 32) {
+                const int i0 = b0 - r0 + q / w1, i1 = b1 - r1 + q % w1;
+                if (i0 < 0 || i0 >= NL || i1 < 0 || i1 >= NL) continue;
+                const int lo = p.cs_grid[i0 * NL + i1], hi = p.cs_grid[i0 * NL + i1 + 1];
+                for (int c = lo; c < hi; c++) {
+                    long long like = curve[0][OFF + i0] + curve[1][OFF + i1];
+#pragma unroll
+                    for (int pr = 2; pr < P; pr++) like += curve[pr][OFF + p.cs_idx[pr * p.n_cand + c]];
+                    const int cell = p.cs_cell[c];
+                    if (like > bb.v || (like == bb.v && cell < bb.i)) { bb.v = like; bb.i = cell; }
+                }
+            }
+            return warp_best(bb);
+        };
+        auto bound = [&](float pk, int r) -> long long { return r <= 2 * L ? __float2ll_rz(__fmul_rn(pk, gauss_s[r])) : 0; };
+        constexpr int R_FIRST = 2, R_MAX = 12;
+        int how = 0;
+        b = scan_box(R_FIRST, R_FIRST);
+        bool ok = b.v > bound(pk0, R_FIRST + 1) + others0 && b.v > bound(pk1, R_FIRST + 1) + others1;
+        if (!ok && b.v != LLONG_MIN) {          // widen: smallest radii whose outside bound is below what we hold
+            int r0 = -1, r1 = -1;
+            for (int r = R_FIRST; r <= R_MAX && (r0 < 0 || r1 < 0); r++) {
+                if (r0 < 0 && b.v > bound(pk0, r + 1) + others0) r0 = r;
+                if (r1 < 0 && b.v > bound(pk1, r + 1) + others1) r1 = r;
+            }
+            if (r0 >= 0 && r1 >= 0) { b = scan_box(r0, r1); ok = true; how = 1; }
+        }
+        if (!ok) {                               // flat or inconsistent curves: scan every tuple
+            how = 2;
+            b.v = LLONG_MIN; b.i = 0x7fffffff;
+            for (int c = lane; c < p.n_cand; c += 32) {
+                long long like = 0;
+#pragma unroll
+                for (int pr = 0; pr < P; pr++) like += curve[pr][OFF + p.cs_idx[pr * p.n_cand + c]];
+                const int cell = p.cs_cell[c];
+                if (like > b.v || (like == b.v && cell < b.i)) { b.v = like; b.i = cell; }
+            }
+            b = warp_best(b);
+        }
+        if (p.stats && lane == 0) atomicAdd(&p.stats[how], 1ull);
     }
-    b = warp_best(b);
     if (lane == 0) {
-        const int cellidx = p.cand_cell[b.i];
+        const int cellidx = b.i;
         if (p.cell) p.cell[f] = cellidx;
         if (p.highest) p.highest[f] = b.v;
         if (p.xy) {
@@ -277,18 +324,38 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[a][b][c] = 0;
         const uint8_t *ya = pl + aoff, *xb = pl + bal;   // + (ch*2+hl)*PLANE + k0
+        // Hankel reuse: rows g+8 of k-step ks are rows g of k-step ks+2 (8 rows x 8 bytes = 64 bytes
+        // = two k-steps), so each step loads only the new 8 bytes per y-plane and keeps two in flight.
+        uint32_t yc0[4], yc1[4], yn0[4], yn1[4];          // y-planes: b.hi, b.lo, c.hi, c.lo
+        const uint32_t ya_s = smem_u32(ya);
+        // "+4" comes from a kernel parameter so ptxas cannot prove the two loads adjacent: fused into one
+        // LDS.64 they would need ~7 register moves per plane and step to reach fragment slots 1 and 3.
+        const uint32_t four = (uint32_t)p.opaque_four;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(ya + (2 + q) * PLANE);
+            yc0[q] = w[0]; yc1[q] = w[1]; yn0[q] = w[8]; yn1[q] = w[9];
+        }
 #pragma unroll 3
         for (int ks = 0; ks < G::KSTEPS; ks++) {
             const int k0 = 32 * ks;
-            uint32_t Ybh[4], Ybl[4], Ych[4], Ycl[4], Xah[2], Xal[2], Xbh[2], Xbl[2];
-            load_a(Ybh, ya + 2 * PLANE + k0); load_a(Ybl, ya + 3 * PLANE + k0);
-            load_a(Ych, ya + 4 * PLANE + k0); load_a(Ycl, ya + 5 * PLANE + k0);
+            uint32_t Y[4][4], Xah[2], Xal[2], Xbh[2], Xbl[2];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t addr = ya_s + (2 + q) * PLANE + k0 + 64;
+                Y[q][0] = yc0[q]; Y[q][2] = yc1[q];
+                // two 32-bit loads (not one 64-bit): each lands directly in its fragment slot
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][1]) : "r"(addr));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][3]) : "r"(addr + four));
+                yc0[q] = yn0[q]; yc1[q] = yn1[q]; yn0[q] = Y[q][1]; yn1[q] = Y[q][3];
+            }
             load_b(Xah, xb + 0 * PLANE + k0, bsh); load_b(Xal, xb + 1 * PLANE + k0, bsh);
             load_b(Xbh, xb + 2 * PLANE + k0, bsh); load_b(Xbl, xb + 3 * PLANE + k0, bsh);
-            mma_s8_s8(acc[0][0], Ybh, Xah); mma_s8_u8(acc[0][1], Ybh, Xal); mma_u8_u8(acc[0][2], Ybl, Xal);
-            mma_s8_s8(acc[1][0], Ych, Xah); mma_s8_u8(acc[1][1], Ych, Xal); mma_u8_u8(acc[1][2], Ycl, Xal);
-            mma_s8_s8(acc[2][0], Ych, Xbh); mma_s8_u8(acc[2][1], Ych, Xbl); mma_u8_u8(acc[2][2], Ycl, Xbl);
-            mma_u8_s8(acc[0][1], Ybl, Xah); mma_u8_s8(acc[1][1], Ycl, Xah); mma_u8_s8(acc[2][1], Ycl, Xbh);
+            // Y[0] = b.hi, Y[1] = b.lo, Y[2] = c.hi, Y[3] = c.lo
+            mma_s8_s8(acc[0][0], Y[0], Xah); mma_s8_u8(acc[0][1], Y[0], Xal); mma_u8_u8(acc[0][2], Y[1], Xal);
+            mma_s8_s8(acc[1][0], Y[2], Xah); mma_s8_u8(acc[1][1], Y[2], Xal); mma_u8_u8(acc[1][2], Y[3], Xal);
+            mma_s8_s8(acc[2][0], Y[2], Xbh); mma_s8_u8(acc[2][1], Y[2], Xbl); mma_u8_u8(acc[2][2], Y[3], Xbl);
+            mma_u8_s8(acc[0][1], Y[1], Xah); mma_u8_s8(acc[1][1], Y[3], Xah); mma_u8_s8(acc[2][1], Y[3], Xbh);
         }
 
         // ---- recombine in int64, arg-max per pair (correlations.c:20-23)

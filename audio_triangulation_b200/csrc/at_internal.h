@@ -27,7 +27,13 @@ struct AtFusedParams {
     const uint8_t *lut;      // [P][cells]
     const uint8_t *cand_idx; // [P][n_cand] distinct lag-index tuples of the LUT
     const int32_t *cand_cell;// [n_cand] first row-major cell of each tuple, ascending
+    // the same tuples sorted by (index of pair 0, index of pair 1) for the bounded search:
+    const uint8_t *cs_idx;   // [P][n_cand]
+    const int32_t *cs_cell;  // [n_cand] first row-major cell of the tuple
+    const int32_t *cs_grid;  // [NL*NL + 1] start offset of the tuples with (i0, i1); last = n_cand
+    unsigned long long *stats; // optional [3]: frames resolved by the first box / a wider box / the full scan
     int32_t n_cand, n_cells, half_w, half_h;
+    int32_t opaque_four;     // always 4; see at_fused_imma.cu
     float px_per_m;
     unsigned long long now_us;
 };

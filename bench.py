@@ -204,6 +204,17 @@ def run_ours(args):
     total_ms, kern_ms = t.tolist()
     value = world * F * args.steps / (total_ms * 1e-3)
 
+    # ---- how the (exact) bounded likelihood search resolved the frames of this batch (untimed extra pass)
+    search = None
+    try:
+        st = loc.localize_device(adc, None, want=WANT + ("stats",))["stats"]
+        torch.cuda.synchronize(dev)
+        st = st.cpu().numpy().astype(float)
+        if st.sum() > 0:
+            search = {"first_box": st[0] / st.sum(), "widened_box": st[1] / st.sum(), "full_scan": st[2] / st.sum()}
+    except Exception:
+        pass
+
     # ---- end to end through the host API: pinned host frames -> H2D -> kernels -> D2H results, every step
     pinned = torch.empty((F, 3, 1024), dtype=torch.uint8).pin_memory()
     pinned.copy_(adc, non_blocking=False)
@@ -267,7 +278,7 @@ def run_ours(args):
                 "config": {"workload": "BASELINE configs[1]: 2^20 synthetic frames per GPU, reference geometry "
                                        "(3 mics x 1024 samples, +-46 lags, 50 kHz), fixed-point direct xcorr, "
                                        "outputs lags+cell+xy", "frames_per_gpu": F, "global_frames": world * F,
-                           "kernel": kernel_used, "l2": "inputs (3.2 GB/GPU) larger than L2, no flush",
+                           "kernel": kernel_used, "likelihood_search": search, "l2": "inputs (3.2 GB/GPU) larger than L2, no flush",
                            "sharding": "contiguous frame ranges, lags gathered to rank 0 over NCCL" if world > 1 else "single GPU"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * BYTES_IN_PER_FRAME,
