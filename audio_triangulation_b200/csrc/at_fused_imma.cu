@@ -20,6 +20,7 @@
 // B: aligned 4-byte loads + funnel shift for the per-column byte offset), then finds the three
 // arg-max lags with warp shuffles.  No block-level synchronisation after start-up.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "at_fused_common.cuh"
 
@@ -43,7 +44,6 @@ struct ImmaSmem {
     float gauss[2 * L + 1];
     alignas(16) uint8_t plane[WARPS][3][2][G::PLANE]; // [warp][channel][hi, lo]
     alignas(8) long long curve[WARPS][3][G::NJ];      // epilogue scratch
-    int best[WARPS][4];
 };
 
 // D += A * B, m16n8k32, int8 operands with per-operand signedness, int32 accumulate
@@ -79,6 +79,20 @@ __device__ __forceinline__ int sext_byte(uint32_t w)
     return r;
 }
 
+// a = two unsigned 16-bit halves, b = four signed bytes: a.lo*b0 + a.hi*b1 (lo) / a.lo*b2 + a.hi*b3 (hi)
+__device__ __forceinline__ int dp2a_lo_u16s8(uint32_t a, uint32_t b)
+{
+    int r;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(0));
+    return r;
+}
+__device__ __forceinline__ int dp2a_hi_u16s8(uint32_t a, uint32_t b)
+{
+    int r;
+    asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(0));
+    return r;
+}
+
 // B fragment (32 x 8, column n = x shifted by n bytes): three aligned words + funnel shift
 __device__ __forceinline__ void load_b(uint32_t (&b)[2], const uint8_t *plane_k0_bal, int bsh)
 {
@@ -88,27 +102,51 @@ __device__ __forceinline__ void load_b(uint32_t (&b)[2], const uint8_t *plane_k0
     b[1] = __funnelshift_r(w1, w2, bsh);
 }
 
-// Warp-scope epilogue for the optional products; curve[][] holds raw sums indexed by j = s + PAD.
+// 64-bit maximum across the warp with two REDUX instructions (high word signed, low word unsigned).
+__device__ __forceinline__ long long warp_max_i64(long long key)
+{
+    const int hi = (int)(key >> 32);
+    const unsigned lo = (unsigned)key;
+    const int mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    return ((long long)mhi << 32) | (long long)mlo;
+}
+
+// Warp-scope epilogue for the optional products; curve[][] holds raw sums indexed by j = s + PAD,
+// b0..b2 are the three best shifts (warp-uniform).
 template <int L, int PAD, int NJ>
-__device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], const int *best, const float *gauss_s,
+__device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], int b0s, int b1s, int b2s, const float *gauss_s,
                                               const AtFusedParams &p, unsigned long long f, int lane)
 {
     constexpr int P = 3, NL = 2 * L + 1, OFF = PAD - L;
+    const int best[3] = {b0s, b1s, b2s};
     if (p.gate && lane == 0) {                                   // sample_compute.h:124-134
-        const int tot = best[0] * best[0] + best[1] * best[1] + best[2] * best[2];
+        const int tot = b0s * b0s + b1s * b1s + b2s * b2s;
         p.gate[f] = tot > 4 ? 1 : 0;
     }
     if (p.raw)
         for (int idx = lane; idx < P * NL; idx += 32) p.raw[f * (unsigned long long)(P * NL) + idx] = curve[idx / NL][OFF + idx % NL];
     if (!(p.corr || p.cell || p.highest || p.xy || p.classes)) return;
-    __syncwarp();
-    for (int idx = lane; idx < P * NL; idx += 32) {              // correlations.c:26-33
-        const int pr = idx / NL, li = idx % NL;
-        int d = (li - L) - best[pr];
-        d = d < 0 ? -d : d;
-        curve[pr][OFF + li] = __float2ll_rz(__fmul_rn(__ll2float_rn(curve[pr][OFF + li]), gauss_s[d]));
+    // Gaussian re-weighting (correlations.c:26-33): in place when whole curves are wanted, otherwise
+    // evaluated on demand for the few entries the bounded likelihood search touches.
+    const bool weighted = p.corr || p.classes;
+    if (weighted) {
+        __syncwarp();
+        for (int idx = lane; idx < P * NL; idx += 32) {
+            const int pr = idx / NL, li = idx % NL;
+            int d = (li - L) - best[pr];
+            d = d < 0 ? -d : d;
+            curve[pr][OFF + li] = __float2ll_rz(__fmul_rn(__ll2float_rn(curve[pr][OFF + li]), gauss_s[d]));
+        }
+        __syncwarp();
     }
-    __syncwarp();
+    auto post = [&](int pr, int li) -> long long {
+        const long long v = curve[pr][OFF + li];
+        if (weighted) return v;
+        int d = (li - L) - (pr == 0 ? b0s : (pr == 1 ? b1s : b2s));
+        d = d < 0 ? -d : d;
+        return __float2ll_rz(__fmul_rn(__ll2float_rn(v), gauss_s[d]));
+    };
     if (p.corr) {
         if (p.corr_struct) {
             long long *base = reinterpret_cast<long long *>(p.corr) + f * (unsigned long long)(P * (NL + 2));
@@ -129,12 +167,12 @@ __device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], const int 
     // a likelihood already found inside it once  bound(r+1) + sum(other Pmax) < that likelihood.
     Best b = {LLONG_MIN, 0x7fffffff};   // .i holds the CELL index here (lower cell wins ties)
     {
-        const int b0 = best[0] + L, b1 = best[1] + L;
+        const int b0 = b0s + L, b1 = b1s + L;
         long long pmax[P];
         long long others0 = 0, others1 = 0;
 #pragma unroll
         for (int pr = 0; pr < P; pr++) {
-            const long long v = curve[pr][OFF + best[pr] + L];
+            const long long v = post(pr, best[pr] + L);
             pmax[pr] = v > 0 ? v : 0;
             if (pr != 0) others0 += pmax[pr];
             if (pr != 1) others1 += pmax[pr];
@@ -147,10 +185,10 @@ __device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], const int 
                 const int i0 = b0 - r0 + q / w1, i1 = b1 - r1 + q % w1;
                 if (i0 < 0 || i0 >= NL || i1 < 0 || i1 >= NL) continue;
                 const int lo = p.cs_grid[i0 * NL + i1], hi = p.cs_grid[i0 * NL + i1 + 1];
+                if (lo == hi) continue;
+                const long long base01 = post(0, i0) + post(1, i1);
                 for (int c = lo; c < hi; c++) {
-                    long long like = curve[0][OFF + i0] + curve[1][OFF + i1];
-#pragma unroll
-                    for (int pr = 2; pr < P; pr++) like += curve[pr][OFF + p.cs_idx[pr * p.n_cand + c]];
+                    const long long like = base01 + post(2, p.cs_idx[2 * p.n_cand + c]);
                     const int cell = p.cs_cell[c];
                     if (like > bb.v || (like == bb.v && cell < bb.i)) { bb.v = like; bb.i = cell; }
                 }
@@ -176,7 +214,7 @@ __device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], const int 
             for (int c = lane; c < p.n_cand; c += 32) {
                 long long like = 0;
 #pragma unroll
-                for (int pr = 0; pr < P; pr++) like += curve[pr][OFF + p.cs_idx[pr * p.n_cand + c]];
+                for (int pr = 0; pr < P; pr++) like += post(pr, p.cs_idx[pr * p.n_cand + c]);
                 const int cell = p.cs_cell[c];
                 if (like > b.v || (like == b.v && cell < b.i)) { b.v = like; b.i = cell; }
             }
@@ -276,10 +314,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
 #pragma unroll
                     for (int w4 = 0; w4 < 4; w4++) {
                         const uint32_t d = __vsub4(rw[w4], m4);      // (b - mean) mod 256, per byte
-                        const int a0 = sext_byte<0x8880>(d), a1 = sext_byte<0x9991>(d);
-                        const int a2 = sext_byte<0xaaa2>(d), a3 = sext_byte<0xbbb3>(d);
-                        const int p0 = a0 * (int)(ww[2 * w4] & 0xFFFFu), p1 = a1 * (int)(ww[2 * w4] >> 16);
-                        const int p2 = a2 * (int)(ww[2 * w4 + 1] & 0xFFFFu), p3 = a3 * (int)(ww[2 * w4 + 1] >> 16);
+                        // IDP.2A does byte extraction, sign extension and the multiply in one instruction:
+                        // (u16 pair) . (s8 pair) with one u16 zeroed selects a single signed byte of d
+                        const int p0 = dp2a_lo_u16s8(ww[2 * w4] & 0x0000FFFFu, d), p1 = dp2a_lo_u16s8(ww[2 * w4] & 0xFFFF0000u, d);
+                        const int p2 = dp2a_hi_u16s8(ww[2 * w4 + 1] & 0x0000FFFFu, d), p3 = dp2a_hi_u16s8(ww[2 * w4 + 1] & 0xFFFF0000u, d);
                         // prepared sample = bits 8..23 of the product: low byte = byte 1, high byte = byte 2
                         const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
                         const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
@@ -358,26 +396,27 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
             mma_u8_s8(acc[0][1], Y[1], Xah); mma_u8_s8(acc[1][1], Y[3], Xah); mma_u8_s8(acc[2][1], Y[3], Xbh);
         }
 
-        // ---- recombine in int64, arg-max per pair (correlations.c:20-23)
+        // ---- recombine in int64, arg-max per pair (correlations.c:20-23): key = value * 128 + (127 - j),
+        //      so the 64-bit maximum is the largest value and, among equals, the lowest lag
         int best3[3];
 #pragma unroll
         for (int pr = 0; pr < 3; pr++) {
-            Best b = {LLONG_MIN, 0x7fffffff};
+            long long key = LLONG_MIN;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
                 const long long v = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i] + (long long)acc[pr][2][i];
                 if (extras && j < G::NJ) s.curve[warp][pr][j] = v;
-                if (j >= PAD - L && j <= PAD + L && v > b.v) { b.v = v; b.i = j; }
+                const long long k = v * 128 + (127 - j);
+                if (j >= PAD - L && j <= PAD + L && k > key) key = k;
             }
-            b = warp_best(b);
-            best3[pr] = b.i - PAD;
+            key = warp_max_i64(key);
+            best3[pr] = 127 - (int)(key & 127) - PAD;
         }
         if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? best3[0] : (lane == 1 ? best3[1] : best3[2]);
         if (extras) {
-            if (lane == 0) { s.best[warp][0] = best3[0]; s.best[warp][1] = best3[1]; s.best[warp][2] = best3[2]; }
             __syncwarp();
-            epilogue_warp<L, PAD, G::NJ>(s.curve[warp], s.best[warp], s.gauss, p, f, lane);
+            epilogue_warp<L, PAD, G::NJ>(s.curve[warp], best3[0], best3[1], best3[2], s.gauss, p, f, lane);
         }
         __syncwarp();   // planes and scratch are rewritten by the next frame
     }
@@ -415,7 +454,10 @@ bool at_fused_imma_supports(const AtShape &sh)
 cudaError_t at_launch_fused_imma(const AtShape &sh, const AtFusedParams &p, int sm_count, cudaStream_t st)
 {
     if (p.sig16 || sh.n_mics != 3) return cudaErrorInvalidValue;
-    if (sh.n_bits == 10 && sh.max_shift == 46) return atk::launch_imma<10, 46, 4, 4>(p, sm_count, st);
+    if (sh.n_bits == 10 && sh.max_shift == 46) {
+        static const int ctas = getenv("AT_IMMA_CTAS") ? atoi(getenv("AT_IMMA_CTAS")) : 4;   // tuning knob
+        return ctas == 5 ? atk::launch_imma<10, 46, 4, 5>(p, sm_count, st) : atk::launch_imma<10, 46, 4, 4>(p, sm_count, st);
+    }
     if (sh.n_bits == 10 && sh.max_shift == 44) return atk::launch_imma<10, 44, 4, 4>(p, sm_count, st);
     if (sh.n_bits == 12 && sh.max_shift == 46) return atk::launch_imma<12, 46, 4, 1>(p, sm_count, st);
     return cudaErrorInvalidValue;
