@@ -43,7 +43,9 @@ struct ImmaSmem {
     alignas(16) uint16_t win2[G::N];                 // 2 * W[i]: (a * 2W) >> 8 == (a * W) >> 7, byte aligned
     float gauss[2 * L + 1];
     alignas(16) uint8_t plane[WARPS][3][2][G::PLANE]; // [warp][channel][hi, lo]
-    alignas(8) long long curve[WARPS][3][G::NJ];      // epilogue scratch
+    // The epilogue's int64 curves (3 x NJ x 8 bytes) reuse the DATA region [PAD, PAD + N) of this
+    // warp's byte planes 0..2 once the MMA loop is done; the zero pads are never touched.
+    static_assert(G::NJ * 8 <= G::N && G::PAD % 8 == 0, "curve scratch must fit one plane's data region");
 };
 
 // D += A * B, m16n8k32, int8 operands with per-operand signedness, int32 accumulate
@@ -114,18 +116,20 @@ __device__ __forceinline__ long long warp_max_i64(long long key)
 
 // Warp-scope epilogue for the optional products; curve[][] holds raw sums indexed by j = s + PAD,
 // b0..b2 are the three best shifts (warp-uniform).
-template <int L, int PAD, int NJ>
-__device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], int b0s, int b1s, int b2s, const float *gauss_s,
+template <int L, int PAD, int NJ, int CSTRIDE>
+__device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, int b1s, int b2s, const float *gauss_s,
                                               const AtFusedParams &p, unsigned long long f, int lane)
 {
     constexpr int P = 3, NL = 2 * L + 1, OFF = PAD - L;
+    // curve(pr, x): raw sums of pair pr, x = lag index j = s + PAD; rows are CSTRIDE int64 apart
+#define CURVE(pr, x) curve_base[(pr) * CSTRIDE + (x)]
     const int best[3] = {b0s, b1s, b2s};
     if (p.gate && lane == 0) {                                   // sample_compute.h:124-134
         const int tot = b0s * b0s + b1s * b1s + b2s * b2s;
         p.gate[f] = tot > 4 ? 1 : 0;
     }
     if (p.raw)
-        for (int idx = lane; idx < P * NL; idx += 32) p.raw[f * (unsigned long long)(P * NL) + idx] = curve[idx / NL][OFF + idx % NL];
+        for (int idx = lane; idx < P * NL; idx += 32) p.raw[f * (unsigned long long)(P * NL) + idx] = CURVE(idx / NL, OFF + idx % NL);
     if (!(p.corr || p.cell || p.highest || p.xy || p.classes)) return;
     // Gaussian re-weighting (correlations.c:26-33): in place when whole curves are wanted, otherwise
     // evaluated on demand for the few entries the bounded likelihood search touches.
@@ -136,12 +140,12 @@ __device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], int b0s, i
             const int pr = idx / NL, li = idx % NL;
             int d = (li - L) - best[pr];
             d = d < 0 ? -d : d;
-            curve[pr][OFF + li] = __float2ll_rz(__fmul_rn(__ll2float_rn(curve[pr][OFF + li]), gauss_s[d]));
+            CURVE(pr, OFF + li) = __float2ll_rz(__fmul_rn(__ll2float_rn(CURVE(pr, OFF + li)), gauss_s[d]));
         }
         __syncwarp();
     }
     auto post = [&](int pr, int li) -> long long {
-        const long long v = curve[pr][OFF + li];
+        const long long v = CURVE(pr, OFF + li);
         if (weighted) return v;
         int d = (li - L) - (pr == 0 ? b0s : (pr == 1 ? b1s : b2s));
         d = d < 0 ? -d : d;
@@ -152,17 +156,17 @@ __device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], int b0s, i
             long long *base = reinterpret_cast<long long *>(p.corr) + f * (unsigned long long)(P * (NL + 2));
             for (int idx = lane; idx < P * (NL + 2); idx += 32) {
                 const int pr = idx / (NL + 2), k = idx % (NL + 2);
-                base[idx] = k < NL ? curve[pr][OFF + k] : (k == NL ? (long long)(unsigned)best[pr] : (long long)p.now_us);
+                base[idx] = k < NL ? CURVE(pr, OFF + k) : (k == NL ? (long long)(unsigned)best[pr] : (long long)p.now_us);
             }
         } else {
             long long *base = reinterpret_cast<long long *>(p.corr) + f * (unsigned long long)(P * NL);
-            for (int idx = lane; idx < P * NL; idx += 32) base[idx] = curve[idx / NL][OFF + idx % NL];
+            for (int idx = lane; idx < P * NL; idx += 32) base[idx] = CURVE(idx / NL, OFF + idx % NL);
         }
     }
     if (!(p.cell || p.highest || p.xy || p.classes)) return;
-    // vga_heatmap.h:96-108: maximum of L = sum_pairs curve[pair][lut] over the distinct LUT tuples,
+    // vga_heatmap.h:96-108: maximum of L = sum_pairs CURVE(pair, lut) over the distinct LUT tuples,
     // first row-major cell on ties.  Exact bounded search: every entry of curve p is <= Pmax_p =
-    // max(curve[p][best_p], 0), and an entry at distance >= r from the peak is <= trunc(peak * g[r])
+    // max(CURVE(p, best_p), 0), and an entry at distance >= r from the peak is <= trunc(peak * g[r])
     // (the re-weighting is monotone), so tuples outside a box around (best_0, best_1) cannot reach
     // a likelihood already found inside it once  bound(r+1) + sum(other Pmax) < that likelihood.
     Best b = {LLONG_MIN, 0x7fffffff};   // .i holds the CELL index here (lower cell wins ties)
@@ -238,11 +242,12 @@ __device__ __forceinline__ void epilogue_warp(long long (*curve)[NJ], int b0s, i
         for (int c = lane; c < p.n_cells; c += 32) {
             long long like = 0;
 #pragma unroll
-            for (int pr = 0; pr < P; pr++) like += curve[pr][OFF + p.lut[pr * p.n_cells + c]];
+            for (int pr = 0; pr < P; pr++) like += CURVE(pr, OFF + p.lut[pr * p.n_cells + c]);
             p.classes[f * (unsigned long long)p.n_cells + c] = like >= tw ? 15 : like >= tg ? 3 : like >= tr ? 8 : like >= tb ? 5 : 0;
         }
     }
 }
+#undef CURVE
 
 template <int NBITS, int L, int WARPS, int CTAS_PER_SM>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(const AtFusedParams p)
@@ -353,6 +358,12 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                     (int16_t)(((int)(signed char)plane(ch, 0)[PAD + i] << 8) | plane(ch, 1)[PAD + i]);
             }
 
+        // next frame of this warp -> L1/L2 while the tensor pipe works (takes HBM latency off the chain)
+        if (f + stride < p.n_frames) {
+            const uint8_t *nx = p.adc + (f + stride) * (unsigned long long)(3 * N) + lane * 128;
+            if (lane * 128 < 3 * N) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+            if (3 * N > 4096 && lane * 128 + 4096 < 3 * N) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 4096));
+        }
         // ---- 33 k-steps x 12 IMMA: pairs (a,b), (a,c), (b,c); x = first, y = second mic
         int acc[3][3][4];
 #pragma unroll
@@ -396,6 +407,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
             mma_u8_s8(acc[0][1], Y[1], Xah); mma_u8_s8(acc[1][1], Y[3], Xah); mma_u8_s8(acc[2][1], Y[3], Xbh);
         }
 
+        __syncwarp();   // every lane is done reading the planes: their data regions now hold the curves
+        constexpr int CSTRIDE = PLANE / 8;                       // int64 stride between planes 0, 1, 2
+        long long *const curve_base = reinterpret_cast<long long *>(pl + PAD);
         // ---- recombine in int64, arg-max per pair (correlations.c:20-23): key = value * 128 + (127 - j),
         //      so the 64-bit maximum is the largest value and, among equals, the lowest lag
         int best3[3];
@@ -406,7 +420,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
             for (int i = 0; i < 4; i++) {
                 const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
                 const long long v = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i] + (long long)acc[pr][2][i];
-                if (extras && j < G::NJ) s.curve[warp][pr][j] = v;
+                if (extras && j < G::NJ) curve_base[pr * CSTRIDE + j] = v;
                 const long long k = v * 128 + (127 - j);
                 if (j >= PAD - L && j <= PAD + L && k > key) key = k;
             }
@@ -416,7 +430,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
         if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? best3[0] : (lane == 1 ? best3[1] : best3[2]);
         if (extras) {
             __syncwarp();
-            epilogue_warp<L, PAD, G::NJ>(s.curve[warp], best3[0], best3[1], best3[2], s.gauss, p, f, lane);
+            epilogue_warp<L, PAD, G::NJ, CSTRIDE>(curve_base, best3[0], best3[1], best3[2], s.gauss, p, f, lane);
         }
         __syncwarp();   // planes and scratch are rewritten by the next frame
     }
