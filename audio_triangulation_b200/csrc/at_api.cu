@@ -74,7 +74,7 @@ struct at_context {
     cudaStream_t stream = nullptr;
     // device tables
     float *d_mic_xy = nullptr; uint8_t *d_lut = nullptr; uint8_t *d_cand_idx = nullptr; int32_t *d_cand_cell = nullptr;
-    uint8_t *d_cs_idx = nullptr; int32_t *d_cs_cell = nullptr; int32_t *d_cs_grid = nullptr;
+    uint8_t *d_cs_idx = nullptr; int32_t *d_cs_cell = nullptr; int32_t *d_cs_grid = nullptr; float2 *d_cell_xy = nullptr;
     int16_t *d_window = nullptr; float *d_gauss = nullptr; int32_t *d_delay_q8 = nullptr;
     // host copies
     std::vector<float> h_mic_xy; std::vector<uint8_t> h_lut; std::vector<int32_t> h_delay_q8;
@@ -123,7 +123,7 @@ extern "C" void at_destroy(at_context *c)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
-                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid};
+                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -162,6 +162,8 @@ static int create_impl(const at_config *cfg, at_context *c)
     CU(cudaMalloc(&c->d_lut, (size_t)c->n_pairs * c->n_cells));
     CU(at_launch_lut_build(c->d_mic_xy, M, L, cfg->sample_rate_hz, cfg->speed_of_sound, cfg->half_w, cfg->half_h,
                            cfg->px_per_m, cfg->height_m, c->d_lut, c->stream));
+    CU(cudaMalloc(&c->d_cell_xy, sizeof(float2) * c->n_cells));
+    CU(at_launch_cell_xy(cfg->half_w, cfg->half_h, cfg->px_per_m, c->d_cell_xy, c->stream));
     c->h_mic_xy.resize(2 * M);
     c->h_lut.resize((size_t)c->n_pairs * c->n_cells);
     CU(cudaMemcpyAsync(c->h_mic_xy.data(), c->d_mic_xy, sizeof(float) * 2 * M, cudaMemcpyDeviceToHost, c->stream));
@@ -299,6 +301,9 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
     p.cand_idx = c->d_cand_idx; p.cand_cell = c->d_cand_cell;
     p.cs_idx = c->d_cs_idx; p.cs_cell = c->d_cs_cell; p.cs_grid = c->d_cs_grid;
     p.opaque_four = 4;
+    p.cell_xy = c->d_cell_xy;
+    static const int dbg = getenv("AT_DEBUG_SKIP") ? atoi(getenv("AT_DEBUG_SKIP")) : 0;   // timing experiments only
+    p.debug_skip = dbg;
     p.n_cand = c->n_cand; p.n_cells = c->n_cells; p.half_w = c->cfg.half_w; p.half_h = c->cfg.half_h;
     p.px_per_m = c->cfg.px_per_m;
     if (kernel == AT_KERNEL_AUTO) kernel = at_fused_imma_supports(sh) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;

@@ -59,6 +59,15 @@ __global__ void lut_build_kernel(const float *mic_xy, int n_mics, int L, float r
         }
 }
 
+// ref: components/vga/vga_heatmap.h:52-53 -- plane coordinates of every cell (IEEE division, as the host does)
+__global__ void cell_xy_kernel(int half_w, int half_h, float px_per_m, float2 *xy)
+{
+    const int W = 2 * half_w + 1, cells = W * (2 * half_h + 1);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    xy[c] = make_float2(__fdiv_rn((float)(c % W - half_w), px_per_m), __fdiv_rn((float)(half_h - c / W), px_per_m));
+}
+
 // ------------------------------------------------------------------ drop-in stage kernels
 // ref: components/rolling_buffer.c:43-71 for an arbitrary int16 ring (single block).
 __global__ void write_out_kernel(const int16_t *ring, int head, int n_bits, int16_t *out, long long *power)
@@ -318,6 +327,14 @@ cudaError_t at_launch_lut_build(const float *d_mic_xy, int n_mics, int L, float 
     const int cells = (2 * half_w + 1) * (2 * half_h + 1);
     lut_build_kernel<<<(cells + 127) / 128, 128, 0, st>>>(d_mic_xy, n_mics, L, rate_hz, speed, half_w, half_h,
                                                           px_per_m, height, d_lut);
+    at_count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t at_launch_cell_xy(int half_w, int half_h, float px_per_m, float2 *d_xy, cudaStream_t st)
+{
+    const int cells = (2 * half_w + 1) * (2 * half_h + 1);
+    cell_xy_kernel<<<(cells + 127) / 128, 128, 0, st>>>(half_w, half_h, px_per_m, d_xy);
     at_count_launch();
     return cudaGetLastError();
 }

@@ -40,7 +40,9 @@ struct ImmaGeo {
 template <int NBITS, int L, int WARPS>
 struct ImmaSmem {
     using G = ImmaGeo<NBITS, L>;
-    alignas(16) uint16_t win2[G::N];                 // 2 * W[i]: (a * 2W) >> 8 == (a * W) >> 7, byte aligned
+    // 2 * W[i] ((a * 2W) >> 8 == (a * W) >> 7, byte aligned), one 32-bit word per sample already masked
+    // for IDP.2A: even samples hold 2W in the low half, odd samples in the high half, other half zero.
+    alignas(16) uint32_t win2[G::N];
     float gauss[2 * L + 1];
     alignas(16) uint8_t plane[WARPS][3][2][G::PLANE]; // [warp][channel][hi, lo]
     // The epilogue's int64 curves (3 x NJ x 8 bytes) reuse the DATA region [PAD, PAD + N) of this
@@ -95,6 +97,13 @@ __device__ __forceinline__ int dp2a_hi_u16s8(uint32_t a, uint32_t b)
     return r;
 }
 
+// four independent byte additions x + k (mod 256): k7 = low 7 bits of k per byte, kM = top bits of k
+__device__ __forceinline__ uint32_t sub_bytes(uint32_t x, uint32_t k7, uint32_t kM)
+{
+    const uint32_t t = (x & 0x7F7F7F7Fu) + k7;
+    return t ^ (x & 0x80808080u) ^ kM;
+}
+
 // B fragment (32 x 8, column n = x shifted by n bytes): three aligned words + funnel shift
 __device__ __forceinline__ void load_b(uint32_t (&b)[2], const uint8_t *plane_k0_bal, int bsh)
 {
@@ -112,6 +121,15 @@ __device__ __forceinline__ long long warp_max_i64(long long key)
     const int mhi = __reduce_max_sync(0xffffffffu, hi);
     const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
     return ((long long)mhi << 32) | (long long)mlo;
+}
+
+// (largest value, then lowest cell) across the warp with three REDUX-class reductions
+__device__ __forceinline__ Best warp_best_cell(Best x)
+{
+    const long long top = warp_max_i64(x.v);
+    const int cell = __reduce_min_sync(0xffffffffu, x.v == top ? x.i : 0x7fffffff);
+    Best r = {top, cell};
+    return r;
 }
 
 // Warp-scope epilogue for the optional products; curve[][] holds raw sums indexed by j = s + PAD,
@@ -197,7 +215,7 @@ __device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, in
                     if (like > bb.v || (like == bb.v && cell < bb.i)) { bb.v = like; bb.i = cell; }
                 }
             }
-            return warp_best(bb);
+            return warp_best_cell(bb);
         };
         auto bound = [&](float pk, int r) -> long long { return r <= 2 * L ? __float2ll_rz(__fmul_rn(pk, gauss_s[r])) : 0; };
         constexpr int R_FIRST = 2, R_MAX = 12;
@@ -222,7 +240,7 @@ __device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, in
                 const int cell = p.cs_cell[c];
                 if (like > b.v || (like == b.v && cell < b.i)) { b.v = like; b.i = cell; }
             }
-            b = warp_best(b);
+            b = warp_best_cell(b);
         }
         if (p.stats && lane == 0) atomicAdd(&p.stats[how], 1ull);
     }
@@ -230,11 +248,7 @@ __device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, in
         const int cellidx = b.i;
         if (p.cell) p.cell[f] = cellidx;
         if (p.highest) p.highest[f] = b.v;
-        if (p.xy) {
-            const int W = 2 * p.half_w + 1;
-            p.xy[2 * f + 0] = __fdiv_rn((float)(cellidx % W - p.half_w), p.px_per_m);
-            p.xy[2 * f + 1] = __fdiv_rn((float)(p.half_h - cellidx / W), p.px_per_m);
-        }
+        if (p.xy) reinterpret_cast<float2 *>(p.xy)[f] = p.cell_xy[cellidx];   // vga_heatmap.h:52-53, tabulated per cell
     }
     if (p.classes) {                                             // vga_heatmap.h:111-126
         const long long top = b.v;
@@ -263,7 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
     // one-time CTA setup: zero every plane (the pads stay zero), doubled window, Gaussian factors
     for (int i = tid; i < (int)(sizeof(s.plane) / 16); i += WARPS * 32)
         reinterpret_cast<uint4 *>(&s.plane[0][0][0][0])[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < N; i += WARPS * 32) s.win2[i] = (uint16_t)(2 * (int)p.window[i]);
+    for (int i = tid; i < N; i += WARPS * 32) s.win2[i] = (uint32_t)(2 * (int)p.window[i]) << ((i & 1) * 16);
     for (int i = tid; i < 2 * L + 1; i += WARPS * 32) s.gauss[i] = p.gauss[i];
     __syncthreads();
 
@@ -295,8 +309,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                 sum = __dp4a(v.x, 0x01010101u, sum); sum = __dp4a(v.y, 0x01010101u, sum);
                 sum = __dp4a(v.z, 0x01010101u, sum); sum = __dp4a(v.w, 0x01010101u, sum);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sum = __reduce_add_sync(0xffffffffu, sum);
             mean[ch] = (int)(sum >> NBITS);
         }
 
@@ -304,7 +317,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
         //      (int16)((b - mean) << 8) = 256 * sext8(b - mean);  ((256 a) * W) >> 15 = (a * 2W) >> 8
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            const uint32_t m4 = (uint32_t)(mean[ch] & 0xFF) * 0x01010101u;
+            // per-byte x - mean (mod 256) = x + k with k = 256 - mean: add the low 7 bits, xor the top bits
+            const uint32_t k4 = (uint32_t)((256 - mean[ch]) & 0xFF) * 0x01010101u;
+            const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
 #pragma unroll
             for (int q = 0; q < Q; q++) {
                 const int j0 = q * 512 + lane * 16;                   // ring slot of this lane's 16 bytes
@@ -312,17 +327,15 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                 const uint32_t rw[4] = {v.x, v.y, v.z, v.w};
                 if ((head & 15) == 0) {
                     const int i0 = (j0 - head) & (N - 1);             // chronological index, 16-aligned
-                    const uint4 wa = *reinterpret_cast<const uint4 *>(&s.win2[i0]);
-                    const uint4 wb = *reinterpret_cast<const uint4 *>(&s.win2[i0 + 8]);
-                    const uint32_t ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int w4 = 0; w4 < 4; w4++) {
-                        const uint32_t d = __vsub4(rw[w4], m4);      // (b - mean) mod 256, per byte
+                        const uint4 ww = *reinterpret_cast<const uint4 *>(&s.win2[i0 + 4 * w4]);
+                        const uint32_t d = sub_bytes(rw[w4], k7, kM);   // (b - mean) mod 256, per byte
                         // IDP.2A does byte extraction, sign extension and the multiply in one instruction:
-                        // (u16 pair) . (s8 pair) with one u16 zeroed selects a single signed byte of d
-                        const int p0 = dp2a_lo_u16s8(ww[2 * w4] & 0x0000FFFFu, d), p1 = dp2a_lo_u16s8(ww[2 * w4] & 0xFFFF0000u, d);
-                        const int p2 = dp2a_hi_u16s8(ww[2 * w4 + 1] & 0x0000FFFFu, d), p3 = dp2a_hi_u16s8(ww[2 * w4 + 1] & 0xFFFF0000u, d);
+                        // (u16 pair) . (s8 pair) with one u16 zero selects a single signed byte of d
+                        const int p0 = dp2a_lo_u16s8(ww.x, d), p1 = dp2a_lo_u16s8(ww.y, d);
+                        const int p2 = dp2a_hi_u16s8(ww.z, d), p3 = dp2a_hi_u16s8(ww.w, d);
                         // prepared sample = bits 8..23 of the product: low byte = byte 1, high byte = byte 2
                         const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
                         const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
@@ -336,7 +349,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                     for (int e = 0; e < 16; e++) {
                         const int i = (j0 + e - head) & (N - 1);
                         const int a = (int)(signed char)(((rw[e >> 2] >> (8 * (e & 3))) - (uint32_t)mean[ch]) & 0xFFu);
-                        const int pr = a * (int)s.win2[i];
+                        const int pr = a * (int)(s.win2[i] >> ((i & 1) * 16));
                         plane(ch, 0)[PAD + i] = (uint8_t)(pr >> 16);
                         plane(ch, 1)[PAD + i] = (uint8_t)(pr >> 8);
                     }
@@ -373,30 +386,26 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[a][b][c] = 0;
         const uint8_t *ya = pl + aoff, *xb = pl + bal;   // + (ch*2+hl)*PLANE + k0
-        // Hankel reuse: rows g+8 of k-step ks are rows g of k-step ks+2 (8 rows x 8 bytes = 64 bytes
-        // = two k-steps), so each step loads only the new 8 bytes per y-plane and keeps two in flight.
-        uint32_t yc0[4], yc1[4], yn0[4], yn1[4];          // y-planes: b.hi, b.lo, c.hi, c.lo
+        // A fragments: four 32-bit loads per y-plane, each landing directly in its fragment register.
+        // On this GPU every instruction issued next to an IMMA costs issue time (legacy mma.sync holds
+        // the dispatch port), so what counts is the instruction total: fusing the loads
+        // into 64-bit ones or re-using the Hankel overlap across k-steps both need register moves that
+        // cost more than the loads they save.  "+4" comes from a kernel parameter so that ptxas cannot
+        // prove two loads adjacent and fuse them.
         const uint32_t ya_s = smem_u32(ya);
-        // "+4" comes from a kernel parameter so ptxas cannot prove the two loads adjacent: fused into one
-        // LDS.64 they would need ~7 register moves per plane and step to reach fragment slots 1 and 3.
-        const uint32_t four = (uint32_t)p.opaque_four;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(ya + (2 + q) * PLANE);
-            yc0[q] = w[0]; yc1[q] = w[1]; yn0[q] = w[8]; yn1[q] = w[9];
-        }
+        const uint32_t ya_4 = ya_s + (uint32_t)p.opaque_four;
 #pragma unroll 3
         for (int ks = 0; ks < G::KSTEPS; ks++) {
+            if (p.debug_skip & 2) break;
             const int k0 = 32 * ks;
             uint32_t Y[4][4], Xah[2], Xal[2], Xbh[2], Xbl[2];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const uint32_t addr = ya_s + (2 + q) * PLANE + k0 + 64;
-                Y[q][0] = yc0[q]; Y[q][2] = yc1[q];
-                // two 32-bit loads (not one 64-bit): each lands directly in its fragment slot
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][1]) : "r"(addr));
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][3]) : "r"(addr + four));
-                yc0[q] = yn0[q]; yc1[q] = yn1[q]; yn0[q] = Y[q][1]; yn1[q] = Y[q][3];
+                const uint32_t off = (2 + q) * PLANE + k0;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][0]) : "r"(ya_s + off));        // row g,   k 0..3
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][2]) : "r"(ya_4 + off));        // row g,   k 4..7
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][1]) : "r"(ya_s + off + 64));   // row g+8, k 0..3
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][3]) : "r"(ya_4 + off + 64));   // row g+8, k 4..7
             }
             load_b(Xah, xb + 0 * PLANE + k0, bsh); load_b(Xal, xb + 1 * PLANE + k0, bsh);
             load_b(Xbh, xb + 2 * PLANE + k0, bsh); load_b(Xbl, xb + 3 * PLANE + k0, bsh);

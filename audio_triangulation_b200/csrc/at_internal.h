@@ -31,9 +31,11 @@ struct AtFusedParams {
     const uint8_t *cs_idx;   // [P][n_cand]
     const int32_t *cs_cell;  // [n_cand] first row-major cell of the tuple
     const int32_t *cs_grid;  // [NL*NL + 1] start offset of the tuples with (i0, i1); last = n_cand
+    const float2 *cell_xy;   // [n_cells] plane coordinates of each cell (vga_heatmap.h:52-53), built on the device
     unsigned long long *stats; // optional [3]: frames resolved by the first box / a wider box / the full scan
     int32_t n_cand, n_cells, half_w, half_h;
     int32_t opaque_four;     // always 4; see at_fused_imma.cu
+    int32_t debug_skip;      // profiling knob (env AT_DEBUG_SKIP): bit0 skip prep, bit1 skip MMA loop, bit2 skip epilogue
     float px_per_m;
     unsigned long long now_us;
 };
@@ -51,6 +53,7 @@ cudaError_t at_launch_mics_triangle(float d_ab, float d_bc, float d_ca, int mirr
 cudaError_t at_launch_lut_build(const float *d_mic_xy, int n_mics, int L, float rate_hz, float speed,
                                 int half_w, int half_h, float px_per_m, float height, uint8_t *d_lut,
                                 cudaStream_t st);
+cudaError_t at_launch_cell_xy(int half_w, int half_h, float px_per_m, float2 *d_xy, cudaStream_t st);
 cudaError_t at_launch_write_out(const int16_t *d_ring, int head, int n_bits, int16_t *d_out, long long *d_power,
                                 cudaStream_t st);
 cudaError_t at_launch_shift8(int16_t *d_x, int n, cudaStream_t st);
