@@ -42,7 +42,15 @@ struct ImmaSmem {
     using G = ImmaGeo<NBITS, L>;
     // 2 * W[i] ((a * 2W) >> 8 == (a * W) >> 7, byte aligned), one 32-bit word per sample already masked
     // for IDP.2A: even samples hold 2W in the low half, odd samples in the high half, other half zero.
+    // Stored chunk-interleaved so the lanes of a warp (consecutive 16-sample chunks) read consecutive
+    // 16-byte groups: word index of sample i = (((c >> 5) * 4 + w) * 32 + (c & 31)) * 4 + e with
+    // c = i / 16, w = (i / 4) & 3, e = i & 3.
     alignas(16) uint32_t win2[G::N];
+    static __device__ __forceinline__ int win_index(int i)
+    {
+        const int c = i >> 4, w = (i >> 2) & 3, e = i & 3;
+        return ((((c >> 5) * 4 + w) * 32) + (c & 31)) * 4 + e;
+    }
     float gauss[2 * L + 1];
     alignas(16) uint8_t plane[WARPS][3][2][G::PLANE]; // [warp][channel][hi, lo]
     // The epilogue's int64 curves (3 x NJ x 8 bytes) reuse the DATA region [PAD, PAD + N) of this
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
     // one-time CTA setup: zero every plane (the pads stay zero), doubled window, Gaussian factors
     for (int i = tid; i < (int)(sizeof(s.plane) / 16); i += WARPS * 32)
         reinterpret_cast<uint4 *>(&s.plane[0][0][0][0])[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < N; i += WARPS * 32) s.win2[i] = (uint32_t)(2 * (int)p.window[i]) << ((i & 1) * 16);
+    for (int i = tid; i < N; i += WARPS * 32) s.win2[S::win_index(i)] = (uint32_t)(2 * (int)p.window[i]) << ((i & 1) * 16);
     for (int i = tid; i < 2 * L + 1; i += WARPS * 32) s.gauss[i] = p.gauss[i];
     __syncthreads();
 
@@ -313,6 +321,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
             mean[ch] = (int)(sum >> NBITS);
         }
 
+        if (!(p.debug_skip & 1))
         // ---- DC removal, <<8, window -> hi / lo byte planes (rolling_buffer.c:66, buffer.c:16, :8-9)
         //      (int16)((b - mean) << 8) = 256 * sext8(b - mean);  ((256 a) * W) >> 15 = (a * 2W) >> 8
 #pragma unroll
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int w4 = 0; w4 < 4; w4++) {
-                        const uint4 ww = *reinterpret_cast<const uint4 *>(&s.win2[i0 + 4 * w4]);
+                        const uint4 ww = *reinterpret_cast<const uint4 *>(&s.win2[S::win_index(i0 + 4 * w4)]);
                         const uint32_t d = sub_bytes(rw[w4], k7, kM);   // (b - mean) mod 256, per byte
                         // IDP.2A does byte extraction, sign extension and the multiply in one instruction:
                         // (u16 pair) . (s8 pair) with one u16 zero selects a single signed byte of d
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                     for (int e = 0; e < 16; e++) {
                         const int i = (j0 + e - head) & (N - 1);
                         const int a = (int)(signed char)(((rw[e >> 2] >> (8 * (e & 3))) - (uint32_t)mean[ch]) & 0xFFu);
-                        const int pr = a * (int)(s.win2[i] >> ((i & 1) * 16));
+                        const int pr = a * (int)(s.win2[S::win_index(i)] >> ((i & 1) * 16));
                         plane(ch, 0)[PAD + i] = (uint8_t)(pr >> 16);
                         plane(ch, 1)[PAD + i] = (uint8_t)(pr >> 8);
                     }
@@ -394,9 +403,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
         // prove two loads adjacent and fuse them.
         const uint32_t ya_s = smem_u32(ya);
         const uint32_t ya_4 = ya_s + (uint32_t)p.opaque_four;
+        const int nsteps = (p.debug_skip & 2) ? 0 : G::KSTEPS;   // profiling knob, kept out of the loop body
 #pragma unroll 3
-        for (int ks = 0; ks < G::KSTEPS; ks++) {
-            if (p.debug_skip & 2) break;
+        for (int ks = 0; ks < nsteps; ks++) {
             const int k0 = 32 * ks;
             uint32_t Y[4][4], Xah[2], Xal[2], Xbh[2], Xbl[2];
 #pragma unroll
