@@ -160,7 +160,10 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
 
     # synthetic batch, resident in HBM: this rank's contiguous frame range of the global batch
-    adc, _, _ = loc.synth_device(F, flags=4 if rank == 0 else 0, first_frame=rank * F)
+    from audio_triangulation_b200.sharding import frame_range
+    lo, hi = frame_range(rank, world, world * F)
+    assert hi - lo == F
+    adc, _, _ = loc.synth_device(F, flags=4 if rank == 0 else 0, first_frame=lo)
     out = {}
     gathered = None
     if world > 1 and rank == 0:
@@ -236,17 +239,16 @@ def run_ours(args):
     e2e_value = world * F * e2e_steps / te.item()
     e2e_ok = bool((hout["lags"].numpy() == out["lags"].cpu().numpy()).all())
 
-    # ---- roofline of the dominant (only) kernel: integer MACs against the measured pipe rate
+    # ---- roofline of the dominant (only) kernel
     kernel_used = args.kernel
     ubench = {}
     if rank == 0:
-        for name in ("imad_wide", "imma_s8", "lds"):
+        for name in ("imma_s8", "imad_wide", "dp2a", "lds"):
             try:
                 g, mhz = loc.microbench(name)
-                ubench[name] = {"gops": g, "sm_mhz_est": mhz}
+                ubench[name] = {"gops": g}
             except Exception as e:   # pragma: no cover
                 ubench[name] = {"error": str(e)}
-    achieved = MAC_PER_FRAME * F / (kern_ms * 1e-3) / 1e12     # useful int16 TMAC/s per GPU
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -256,25 +258,36 @@ def run_ours(args):
     hbm_ach = (BYTES_IN_PER_FRAME + BYTES_OUT_PER_FRAME) * F / (kern_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_frame") * F
     except Exception:
         pass
 
     line = None
     if rank == 0:
-        int_peak = ubench.get("imad_wide", {}).get("gops", 0.0) / 1e3   # TMAC/s measured live (IMAD.WIDE chain)
-        roof = {"bound": "int-pipe (IMAD.WIDE); HBM is secondary, see hbm_*", "achieved": achieved,
-                "peak": int_peak, "unit": "TMAC/s (int16 x int16 -> int64)",
-                "frac": achieved / int_peak if int_peak else None, "traffic": traffic,
-                "peak_source": "measured live by at_microbench(IMAD.WIDE) on this GPU; MEASURED_PEAKS.json has no integer-pipe figure",
-                "kernel_ms": kern_ms, "hbm_achieved_gbs": hbm_ach, "hbm_peak_gbs": hbm_peak,
-                "hbm_frac": hbm_ach / hbm_peak,
+        # The auto / imma kernel computes the 279,210 int16 MACs of a frame as 4 x 279,210 int8 MACs on the
+        # tensor cores (byte-split Toeplitz x Hankel tiles); padded to whole 16x8x32 tiles that is 396 IMMA =
+        # 1,622,016 int8 MACs issued.  Peak = legacy mma.sync int8 rate measured live on this GPU
+        # (MEASURED_PEAKS.json carries no int8 figure; its bf16 number is the tcgen05 path this kernel cannot use,
+        # see DESIGN.md).  The imad kernel is measured against the IMAD.WIDE chain rate instead.
+        imma = kernel_used in ("auto", "imma")
+        peak_name = "imma_s8" if imma else "imad_wide"
+        peak = ubench.get(peak_name, {}).get("gops", 0.0) / 1e3
+        per_frame = MAC_PER_FRAME * (4 if imma else 1)
+        achieved = per_frame * F / (kern_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor" if imma else "int-pipe",
+                "achieved": achieved, "peak": peak,
+                "unit": "T int8-MAC/s (4 per int16 MAC, useful lags only)" if imma else "T int16-MAC/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic,
+                "peak_source": "measured live: at_microbench(%s) on this GPU" % peak_name,
+                "issued_frac": (achieved * 1622016 / per_frame / peak) if (imma and peak) else None,
+                "kernel_ms": kern_ms, "algorithmic_mac_per_frame": MAC_PER_FRAME,
+                "hbm_achieved_gbs": hbm_ach, "hbm_peak_gbs": hbm_peak, "hbm_frac": hbm_ach / hbm_peak,
                 "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
-                "microbench": ubench}
+                "microbench_gops": {k: v.get("gops") for k, v in ubench.items()}}
         line = {"metric": "localized frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int16 x int16 -> int64 (u8 ADC in)", "data": "synthetic",
+                "dtype": "int16 x int16 -> int64, computed as 4 x (int8 x int8 -> int32) on tensor cores (u8 ADC in)", "data": "synthetic",
                 "config": {"workload": "BASELINE configs[1]: 2^20 synthetic frames per GPU, reference geometry "
                                        "(3 mics x 1024 samples, +-46 lags, 50 kHz), fixed-point direct xcorr, "
                                        "outputs lags+cell+xy", "frames_per_gpu": F, "global_frames": world * F,
