@@ -269,7 +269,7 @@ def run_ours(args):
         # 1,622,016 int8 MACs issued.  Peak = legacy mma.sync int8 rate measured live on this GPU
         # (MEASURED_PEAKS.json carries no int8 figure; its bf16 number is the tcgen05 path this kernel cannot use,
         # see DESIGN.md).  The imad kernel is measured against the IMAD.WIDE chain rate instead.
-        imma = kernel_used in ("auto", "imma")
+        imma = kernel_used in ("auto", "imma", "imma_lm")
         peak_name = "imma_s8" if imma else "imad_wide"
         peak = ubench.get(peak_name, {}).get("gops", 0.0) / 1e3
         per_frame = MAC_PER_FRAME * (4 if imma else 1)
@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_DEFAULT, help="frames per GPU per step")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "imma"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "imma", "imma_lm"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
