@@ -206,7 +206,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma3_kernel
                     }
             }
         } else {
-            // ring head not 16-aligned: byte-wise stores into every copy (rare; capture heads are arbitrary)
+            // ring head not 16-aligned: byte-wise stores into every copy (rare; capture heads are arbitrary).
+            // The first c bytes of a delayed copy's data region belong to the zero pad; the previous frame's
+            // epilogue may have used that region as scratch, so clear them first.
+            if (lane < 12) *reinterpret_cast<uint32_t *>(sl + G::XC(lane / 3, 1 + lane % 3) + PAD) = 0u;
+            __syncwarp();
             for (int ch = 0; ch < 3; ch++)
                 for (int q = 0; q < 2; q++) {
                     const uint4 v = raw[ch * 2 + q];
