@@ -307,7 +307,7 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
     p.n_cand = c->n_cand; p.n_cells = c->n_cells; p.half_w = c->cfg.half_w; p.half_h = c->cfg.half_h;
     p.px_per_m = c->cfg.px_per_m;
     if (kernel == AT_KERNEL_AUTO)
-        kernel = at_fused_imma3_supports(sh) ? AT_KERNEL_IMMA_LM : at_fused_imma_supports(sh) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;
+        kernel = at_fused_imma_supports(sh) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;   // IMMA_LM measured slower
     cudaError_t e;
     if (kernel == AT_KERNEL_IMMA_LM) {
         if (!at_fused_imma3_supports(sh)) return fail(AT_EINVAL, "IMMA-LM kernel has no instantiation for this shape");
