@@ -176,6 +176,50 @@ class Localizer:
         return int(self.lib.at_kernel_launches())
 
 
+class Stream:
+    """Device-resident capture state of many arrays (at_stream): push sample blocks, get onsets + captured rings."""
+
+    def __init__(self, loc, n_arrays):
+        self.loc, self.n_arrays = loc, n_arrays
+        self.h = C.c_void_p()
+        L.check(loc.lib.at_stream_create(loc.ctx, n_arrays, C.byref(self.h)))
+
+    def close(self):
+        if self.h.value:
+            self.loc.lib.at_stream_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        import torch
+        L.check(self.loc.lib.at_stream_reset(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def push(self, samples, want_frames=True, out=None):
+        """samples: torch.uint8 CUDA [A, ticks, mics].  Returns dict(fired [A] int32 (1-based tick or -1),
+        frames [A, mics, N] uint8 ring order, heads [A] int32); frames/heads rows are valid where fired > 0."""
+        import torch
+        assert samples.is_cuda and samples.dtype == torch.uint8 and samples.is_contiguous()
+        A, ticks = samples.shape[0], samples.shape[1]
+        assert A == self.n_arrays
+        res = {} if out is None else out
+        dev = samples.device
+        if "fired" not in res:
+            res["fired"] = torch.empty(A, dtype=torch.int32, device=dev)
+        if want_frames and "frames" not in res:
+            res["frames"] = torch.zeros((A, self.loc.n_mics, self.loc.n_samples), dtype=torch.uint8, device=dev)
+            res["heads"] = torch.zeros(A, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev)
+        L.check(self.loc.lib.at_stream_push(self.h, samples.data_ptr(), ticks, res["fired"].data_ptr(),
+                                            res["frames"].data_ptr() if want_frames else None,
+                                            res["heads"].data_ptr() if want_frames else None, C.c_void_p(st.cuda_stream)))
+        return res
+
+
 def _host_ptr(a):
     if isinstance(a, np.ndarray):
         assert a.flags["C_CONTIGUOUS"]

@@ -479,6 +479,60 @@ extern "C" int at_heatmap_device(at_context *c, const int64_t *d_corr, size_t n_
     return AT_OK;
 }
 
+// ------------------------------------------------------------------ streaming front end
+struct at_stream {
+    at_context *ctx;
+    size_t n_arrays;
+    uint8_t *d_hist;      // [A][M][N] last N samples per mic, chronological, zero-filled since the last reset
+    long long *d_count;   // [A] pushes since the last reset
+};
+
+extern "C" int at_stream_create(at_context *c, size_t n_arrays, at_stream **out)
+{
+    if (!c || !out || !n_arrays) return fail(AT_EINVAL, "at_stream_create: bad argument");
+    if (c->cfg.n_mics != 3 || c->cfg.n_bits != 10) return fail(AT_EINVAL, "streaming front end: reference shape only (3 mics, 1024 samples)");
+    CU(cudaSetDevice(c->cfg.device));
+    at_stream *s = new at_stream{c, n_arrays, nullptr, nullptr};
+    const size_t hb = n_arrays * (size_t)c->cfg.n_mics * c->n_samples;
+    cudaError_t e = cudaMalloc(&s->d_hist, hb);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_count, n_arrays * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemset(s->d_hist, 0, hb);
+    if (e == cudaSuccess) e = cudaMemset(s->d_count, 0, n_arrays * sizeof(long long));
+    if (e != cudaSuccess) { at_stream_destroy(s); return fail(AT_ECUDA, "at_stream_create: %s", cudaGetErrorString(e)); }
+    *out = s;
+    return AT_OK;
+}
+
+extern "C" void at_stream_destroy(at_stream *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->ctx->cfg.device);
+    if (s->d_hist) cudaFree(s->d_hist);
+    if (s->d_count) cudaFree(s->d_count);
+    delete s;
+}
+
+extern "C" int at_stream_reset(at_stream *s, void *stream)
+{
+    if (!s) return fail(AT_EINVAL, "at_stream_reset: null stream");
+    CU(cudaSetDevice(s->ctx->cfg.device));
+    CU(cudaMemsetAsync(s->d_hist, 0, s->n_arrays * (size_t)s->ctx->cfg.n_mics * s->ctx->n_samples, (cudaStream_t)stream));
+    CU(cudaMemsetAsync(s->d_count, 0, s->n_arrays * sizeof(long long), (cudaStream_t)stream));
+    return AT_OK;
+}
+
+extern "C" int at_stream_push(at_stream *s, const uint8_t *d_samples, size_t n_ticks, int32_t *d_fired_tick, uint8_t *d_frames,
+                              int32_t *d_heads, void *stream)
+{
+    if (!s || !d_samples || !d_fired_tick) return fail(AT_EINVAL, "at_stream_push: null argument");
+    if (n_ticks == 0 || n_ticks > (size_t)s->ctx->n_samples || n_ticks % 16)
+        return fail(AT_EINVAL, "at_stream_push: n_ticks must be a multiple of 16 in [16, %d]", s->ctx->n_samples);
+    CU(cudaSetDevice(s->ctx->cfg.device));
+    CU(at_launch_stream_push(s->ctx->cfg.n_mics, s->ctx->cfg.n_bits, s->n_arrays, n_ticks, d_samples, s->d_hist, s->d_count,
+                             d_fired_tick, d_frames, d_heads, (cudaStream_t)stream));
+    return AT_OK;
+}
+
 // ------------------------------------------------------------------ synthetic frames
 extern "C" int at_synth_host(const at_context *c, uint64_t seed, uint32_t flags, size_t first, size_t n_frames,
                              uint8_t *adc, int32_t *heads, int32_t *true_cell)

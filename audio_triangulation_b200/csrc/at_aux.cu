@@ -197,6 +197,118 @@ __global__ void heatmap_kernel(const long long *corr, int n_pairs, int L, const 
     }
 }
 
+// ------------------------------------------------------------------ streaming front end
+// ref: components/rolling_buffer.c:16-41, :73-85 and the capture loop of sample_compute.h:55-99, for many
+// independent arrays.  The reference's running sums over the newer / older half of the ring are plain window
+// sums of the sample stream, so a block of ticks is processed in parallel: one CTA per array, thread j owns the
+// 16 positions [16j, 16j+16) of the sequence  seq = [ last N samples (zero-filled since the last reset) | new block ],
+// per-thread segment sums -> block prefix -> every thread slides the two half-window sums over its ticks
+// (the windows start 512 / 1024 positions = 32 / 64 segments back, i.e. on other threads' segment boundaries)
+// -> first tick with  out > (2 << 2(n_bits-1)) + in  and all rings full -> block minimum.
+// State per array: hist uint8 [M][N] (chronological), count = pushes since the last reset.
+template <int NMICS, int NBITS>
+__global__ void __launch_bounds__(128) stream_push_kernel(const uint8_t *samples /*[A][ticks][M]*/, int n_ticks, uint8_t *hist,
+                                                          long long *count, int32_t *fired_tick, uint8_t *frames,
+                                                          int32_t *heads)
+{
+    constexpr int N = 1 << NBITS, H = N / 2, SEG = (2 * N) / 128;       // SEG = 16 at N = 1024
+    static_assert(SEG == 16, "one 16-byte segment per thread");
+    __shared__ __align__(16) uint8_t seq[NMICS][2 * N];
+    __shared__ int pre1[NMICS][129];
+    __shared__ int pre2[NMICS][129];
+    __shared__ int first_s;
+    const int tid = threadIdx.x;
+    const size_t a = blockIdx.x;
+    const long long c0 = count[a];
+    const int fill0 = c0 < N ? (int)c0 : N;
+    if (tid == 0) first_s = 0x7fffffff;
+    // stage seq: history (16-byte copies) and the new block (de-interleave [tick][mic])
+    for (int m = 0; m < NMICS; m++) {
+        if (tid < N / 16) reinterpret_cast<uint4 *>(&seq[m][0])[tid] = reinterpret_cast<const uint4 *>(hist + (a * NMICS + m) * N)[tid];
+    }
+    for (int i = tid; i < n_ticks * NMICS; i += 128) seq[i % NMICS][N + i / NMICS] = samples[a * (size_t)n_ticks * NMICS + i];
+    for (int i = tid; i < (N - n_ticks) * NMICS; i += 128) seq[i % NMICS][N + n_ticks + i / NMICS] = 0;
+    __syncthreads();
+    // segment sums and block-wide exclusive prefix (warp scan + cross-warp offsets)
+    int s1[NMICS], s2[NMICS];
+#pragma unroll
+    for (int m = 0; m < NMICS; m++) {
+        const uint4 v = reinterpret_cast<const uint4 *>(&seq[m][0])[tid];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        unsigned t1 = 0, t2 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { t1 = __dp4a(w[k], 0x01010101u, t1); t2 = __dp4a(w[k], w[k], t2); }
+        s1[m] = (int)t1; s2[m] = (int)t2;
+    }
+#pragma unroll
+    for (int m = 0; m < NMICS; m++) {
+        int i1 = s1[m], i2 = s2[m];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u1 = __shfl_up_sync(0xffffffffu, i1, o), u2 = __shfl_up_sync(0xffffffffu, i2, o);
+            if ((tid & 31) >= o) { i1 += u1; i2 += u2; }
+        }
+        pre1[m][tid + 1] = i1; pre2[m][tid + 1] = i2;        // inclusive within the warp, fixed up below
+    }
+    __syncthreads();
+    if (tid < NMICS) {
+        const int m = tid;
+        int o1 = 0, o2 = 0;
+        pre1[m][0] = 0; pre2[m][0] = 0;
+        for (int w = 0; w < 4; w++) {                           // add the totals of the preceding warps
+            const int e1 = pre1[m][32 * w + 32], e2 = pre2[m][32 * w + 32];
+            if (w) for (int k = 1; k <= 32; k++) { pre1[m][32 * w + k] += o1; pre2[m][32 * w + k] += o2; }
+            o1 += e1; o2 += e2;
+        }
+    }
+    __syncthreads();
+    // slide over this thread's ticks: position pos = 16 tid + e  <->  tick t = pos - N
+    if (16 * tid + 15 >= N && 16 * tid < N + n_ticks) {
+        long long cur1[NMICS], cur2[NMICS], mid1[NMICS], mid2[NMICS], old1[NMICS], old2[NMICS];
+#pragma unroll
+        for (int m = 0; m < NMICS; m++) {   // prefix sums S(pos) excluding pos, at pos, pos-512, pos-1024 (segment starts)
+            cur1[m] = pre1[m][tid]; cur2[m] = pre2[m][tid];
+            mid1[m] = pre1[m][tid - 32]; mid2[m] = pre2[m][tid - 32];
+            old1[m] = tid >= 64 ? pre1[m][tid - 64] : 0; old2[m] = tid >= 64 ? pre2[m][tid - 64] : 0;
+        }
+        const long long thr = 2LL << (2 * (NBITS - 1));         // sample_compute.h:21
+        for (int e = 0; e < 16; e++) {
+            const int pos = 16 * tid + e, t = pos - N;
+            long long out = 0, in = 0;
+#pragma unroll
+            for (int m = 0; m < NMICS; m++) {                   // include position pos / pos-512 / pos-1024
+                const int x = seq[m][pos], y = seq[m][pos - H], z = pos >= N ? seq[m][pos - N] : 0;
+                cur1[m] += x; cur2[m] += x * x; mid1[m] += y; mid2[m] += y * y;
+                if (pos >= N) { old1[m] += z; old2[m] += z * z; }
+                const long long it = cur1[m] - mid1[m], ip = cur2[m] - mid2[m];          // newest N/2 samples
+                const long long ot = mid1[m] - old1[m], op = mid2[m] - old2[m];          // the N/2 before them
+                in += ip * H - it * it;                                                  // rolling_buffer.c:73-78
+                out += op * H - ot * ot;                                                 // rolling_buffer.c:80-85
+            }
+            if (t >= 0 && t < n_ticks && fill0 + t + 1 >= N && out > thr + in) { atomicMin(&first_s, t); break; }
+        }
+    }
+    __syncthreads();
+    const int first = first_s;                                    // 0-based tick of the first firing, or INT_MAX
+    if (first == 0x7fffffff) {
+        // no onset: keep the last N samples, chronological
+        for (int m = 0; m < NMICS; m++)
+            for (int i = tid; i < N; i += 128) hist[(a * NMICS + m) * N + i] = seq[m][n_ticks + i];
+        if (tid == 0) { count[a] = c0 + n_ticks; fired_tick[a] = -1; }
+        return;
+    }
+    // onset: emit the ring as the reference holds it (ring order + head), then restart the capture
+    const int head = (int)((c0 + first + 1) & (N - 1));
+    for (int m = 0; m < NMICS; m++)
+        for (int i = tid; i < N; i += 128) {
+            const uint8_t v = seq[m][first + 1 + i];              // chronological sample i of the captured frame
+            if (frames) frames[(a * NMICS + m) * N + ((head + i) & (N - 1))] = v;
+            const int rest = n_ticks - (first + 1);               // ticks after the onset start the next capture
+            hist[(a * NMICS + m) * N + i] = i >= N - rest ? seq[m][N + first + 1 + (i - (N - rest))] : 0;
+        }
+    if (tid == 0) { count[a] = n_ticks - (first + 1); fired_tick[a] = first + 1; if (heads) heads[a] = head; }
+}
+
 // ------------------------------------------------------------------ synthetic frames
 // One thread per 4 consecutive ring slots of one (frame, mic); bytes identical to at_synth_host.
 __global__ void synth_kernel(unsigned long long seed, unsigned flags, unsigned long long first,
@@ -398,6 +510,17 @@ cudaError_t at_launch_synth(unsigned long long seed, unsigned flags, size_t firs
     if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
     synth_kernel<<<(unsigned)blocks, 256, 0, st>>>(seed, flags, first, n_frames, n_mics, n_bits, n_cells, d_delay_q8,
                                                    d_adc, d_heads, d_cell);
+    at_count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t at_launch_stream_push(int n_mics, int n_bits, size_t n_arrays, size_t n_ticks, const uint8_t *d_samples,
+                                  uint8_t *d_hist, long long *d_count, int32_t *d_fired, uint8_t *d_frames, int32_t *d_heads,
+                                  cudaStream_t st)
+{
+    if (!n_arrays) return cudaSuccess;
+    if (n_mics != 3 || n_bits != 10) return cudaErrorInvalidValue;
+    stream_push_kernel<3, 10><<<(unsigned)n_arrays, 128, 0, st>>>(d_samples, (int)n_ticks, d_hist, d_count, d_fired, d_frames, d_heads);
     at_count_launch();
     return cudaGetLastError();
 }

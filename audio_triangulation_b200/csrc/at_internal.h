@@ -74,8 +74,8 @@ cudaError_t at_launch_synth(unsigned long long seed, unsigned flags, size_t firs
                             int n_bits, int n_cells, const int32_t *d_delay_q8, uint8_t *d_adc, int32_t *d_heads,
                             int32_t *d_cell, cudaStream_t st);
 cudaError_t at_launch_stream_push(int n_mics, int n_bits, size_t n_arrays, size_t n_ticks, const uint8_t *d_samples,
-                                  int16_t *d_ring, long long *d_sums, int32_t *d_head_full, int32_t *d_fired,
-                                  uint8_t *d_frames, int32_t *d_heads, cudaStream_t st);
+                                  uint8_t *d_hist, long long *d_count, int32_t *d_fired, uint8_t *d_frames, int32_t *d_heads,
+                                  cudaStream_t st);
 cudaError_t at_run_microbench(int which, int sm_count, double *gops, double *mhz, cudaStream_t st);
 
 void at_count_launch(unsigned n = 1);

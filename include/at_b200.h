@@ -203,6 +203,20 @@ int at_average_device(at_context *ctx, int64_t *d_est, int32_t *d_est_best, uint
 int at_heatmap_device(at_context *ctx, const int64_t *d_corr /*[A][pairs][2L+1]*/, size_t n_arrays,
                       int32_t *d_cell, int64_t *d_highest, float *d_xy, uint8_t *d_classes, void *stream);
 
+/* Streaming front end (ref: components/rolling_buffer.c:16-41, :73-85; capture loop sample_compute.h:55-99) for
+ * n_arrays independent arrays whose ring state lives on the device.  at_stream_push() consumes n_ticks sample triples
+ * per array (n_ticks a multiple of 16, <= frame length, so at most one onset per call) and reports per array the
+ * 1-based tick at which the onset gate fired (-1: not in this block) together with the captured ring (ring order) and
+ * its head, ready for at_localize_device().  After an onset the array's capture restarts with the remaining ticks,
+ * exactly as the reference re-initialises its rings (sample_compute.h:55-57).  Reference shape only. */
+typedef struct at_stream at_stream;
+int at_stream_create(at_context *ctx, size_t n_arrays, at_stream **out);
+void at_stream_destroy(at_stream *s);
+int at_stream_reset(at_stream *s, void *stream);
+int at_stream_push(at_stream *s, const uint8_t *d_samples /*[A][ticks][mics]*/, size_t n_ticks,
+                   int32_t *d_fired_tick /*[A]*/, uint8_t *d_frames /*[A][mics][N], may be NULL*/,
+                   int32_t *d_heads /*[A], may be NULL*/, void *stream);
+
 /* Synthetic multi-channel frames (host harness input; replaces the Pico ADC/DMA capture,
  * ref: components/dma_sampler.c).  Integer-only counter-based generator: the host and device
  * versions emit identical bytes.  true_cell (optional): the source's heat-map cell. */
