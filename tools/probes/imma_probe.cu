@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(128) probe(int iters, int seed, int *sink)
     sbuf[threadIdx.x] = seed; sbuf[threadIdx.x + 128] = seed;
     __syncthreads();
     const unsigned saddr = (unsigned)__cvta_generic_to_shared(&sbuf[threadIdx.x & 31]);
+    const unsigned saddr16 = (unsigned)__cvta_generic_to_shared(&sbuf[4 * (threadIdx.x & 31)]);
+    const unsigned saddr8 = (unsigned)__cvta_generic_to_shared(&sbuf[2 * (threadIdx.x & 31)]);
     for (int i = 0; i < 8; i++) { x[i] = seed + i; xf[i] = seed + i; }
     for (int i = 0; i < 4; i++) {
         for (int j = 0; j < 4; j++) A[i][j] = seed * (i * 4 + j + 1) + threadIdx.x;
@@ -61,6 +63,26 @@ __global__ void __launch_bounds__(128) probe(int iters, int seed, int *sink)
                 if (MODE == 6) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k & 7]) : "r"(seed), "r"(it)); // ALU pipe
                 if (MODE == 7) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(xf[k & 7]) : "f"(1.0001f), "f"(0.5f));  // FFMA
                 if (MODE == 8) asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(x[k & 7]) : "r"(saddr + 4 * (k & 7)));
+            }
+            if (MODE == 9) {     // 4 ldmatrix.x4 per 12 IMMA
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(saddr16 + 512 * k));
+            }
+            if (MODE == 10) {    // 12 LDS.64 per 12 IMMA
+#pragma unroll
+                for (int k = 0; k < 12; k++)
+                    asm volatile("ld.volatile.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x[k & 3]), "=r"(x[4 + (k & 3)]) : "r"(saddr8 + 256 * (k & 7)));
+            }
+            if (MODE == 11) {    // 6 LDS.128 per 12 IMMA
+#pragma unroll
+                for (int k = 0; k < 6; k++)
+                    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(saddr16 + 512 * k));
+            }
+            if (MODE == 12) {    // 24 MOV-like (IMAD.MOV is what ptxas emits) -> use mov via prmt to stay on ALU
+#pragma unroll
+                for (int k = 0; k < 24; k++) asm volatile("prmt.b32 %0, %1, %2, 0x3210;" : "=r"(x[k & 7]) : "r"(x[(k + 1) & 7]), "r"(it));
             }
         }
         // operands change every iteration, like freshly loaded fragments
@@ -109,6 +131,10 @@ int main()
         run<6>("kernel pattern + 24 LOP3 (ALU)", w, sms);
         run<7>("kernel pattern + 24 FFMA", w, sms);
         run<8>("kernel pattern + 24 LDS.32", w, sms);
+        run<9>("kernel pattern + 4 LDSM.x4", w, sms);
+        run<10>("kernel pattern + 12 LDS.64", w, sms);
+        run<11>("kernel pattern + 6 LDS.128", w, sms);
+        run<12>("kernel pattern + 24 PRMT", w, sms);
     }
     return 0;
 }
