@@ -307,14 +307,15 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
     p.n_cand = c->n_cand; p.n_cells = c->n_cells; p.half_w = c->cfg.half_w; p.half_h = c->cfg.half_h;
     p.px_per_m = c->cfg.px_per_m;
     if (kernel == AT_KERNEL_AUTO)
-        kernel = at_fused_imma_supports(sh) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;   // IMMA_LM measured slower
+        kernel = (at_fused_imma_supports(sh) || at_fused_imma_cta_supports(sh)) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;   // IMMA_LM measured slower
     cudaError_t e;
     if (kernel == AT_KERNEL_IMMA_LM) {
         if (!at_fused_imma3_supports(sh)) return fail(AT_EINVAL, "IMMA-LM kernel has no instantiation for this shape");
         e = at_launch_fused_imma3(sh, p, c->sm_count, st);
     } else if (kernel == AT_KERNEL_IMMA) {
-        if (!at_fused_imma_supports(sh)) return fail(AT_EINVAL, "IMMA kernel has no instantiation for this shape");
-        e = at_launch_fused_imma(sh, p, c->sm_count, st);
+        if (at_fused_imma_supports(sh)) e = at_launch_fused_imma(sh, p, c->sm_count, st);             // warp per frame, 3 mics
+        else if (at_fused_imma_cta_supports(sh)) e = at_launch_fused_imma_cta(sh, p, c->sm_count, st); // CTA per frame, M mics
+        else return fail(AT_EINVAL, "IMMA kernel has no instantiation for this shape");
     } else {
         e = at_launch_fused_imad(sh, p, c->sm_count, st);
     }

@@ -47,6 +47,9 @@ cudaError_t at_launch_fused_imad(const AtShape &shape, const AtFusedParams &p, i
 // at_fused_imma.cu
 cudaError_t at_launch_fused_imma(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
 bool at_fused_imma_supports(const AtShape &shape);
+// at_fused_imma_cta.cu -- CTA-per-frame tensor kernel for general arrays (4 / 8 mics, 1024 / 4096 samples)
+cudaError_t at_launch_fused_imma_cta(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
+bool at_fused_imma_cta_supports(const AtShape &shape);
 // at_fused_imma3.cu -- low-instruction-count variant (ldmatrix + delayed plane copies), 1024-sample frames
 cudaError_t at_launch_fused_imma3(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
 bool at_fused_imma3_supports(const AtShape &shape);
