@@ -73,6 +73,7 @@ def load():
         "at_synth_host": (C.c_int, [ctx, u64, C.c_uint32, sz, sz, vp, vp, vp]),
         "at_synth_device": (C.c_int, [ctx, u64, C.c_uint32, sz, sz, vp, vp, vp, vp]),
         "at_microbench": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "at_gccphat_device": (C.c_int, [ctx, vp, vp, sz, vp, vp, vp]),
         "at_stream_create": (C.c_int, [ctx, sz, C.POINTER(ctx)]),
         "at_stream_destroy": (None, [ctx]),
         "at_stream_reset": (C.c_int, [ctx, vp]),

@@ -147,6 +147,18 @@ class Localizer:
                                            g("classes"), C.c_void_p(st.cuda_stream)))
         return res
 
+    def gccphat_device(self, adc, heads=None, want_peak=False, stream=None):
+        """FFT / GCC-PHAT variant of the TDOA stage (crossover study; not a reference algorithm)."""
+        import torch
+        F = adc.shape[0]
+        lags = torch.empty((F, self.n_pairs), dtype=torch.int32, device=adc.device)
+        peak = torch.empty((F, self.n_pairs), dtype=torch.float32, device=adc.device) if want_peak else None
+        st = stream if stream is not None else torch.cuda.current_stream(adc.device)
+        L.check(self.lib.at_gccphat_device(self.ctx, adc.data_ptr(), None if heads is None else heads.data_ptr(), F,
+                                           lags.data_ptr(), None if peak is None else peak.data_ptr(),
+                                           C.c_void_p(st.cuda_stream)))
+        return (lags, peak) if want_peak else lags
+
     # ---- synthetic frames
     def synth_host(self, n_frames, seed=0xA7D10, flags=0, first_frame=0):
         adc = np.empty((n_frames, self.n_mics, self.n_samples), np.uint8)

@@ -81,6 +81,7 @@ struct at_context {
     // staging for the host API and the drop-in symbols
     HostSlot slot[2];
     void *d_scratch = nullptr; size_t scratch_bytes = 0;
+    float2 *d_spec = nullptr; size_t spec_frames = 0;   // GCC-PHAT spectra scratch
 };
 
 static int ensure(void **p, size_t bytes)
@@ -123,7 +124,7 @@ extern "C" void at_destroy(at_context *c)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
-                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy};
+                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -477,6 +478,33 @@ extern "C" int at_heatmap_device(at_context *c, const int64_t *d_corr, size_t n_
     CU(at_launch_heatmap((const long long *)d_corr, n_arrays, c->n_pairs, c->cfg.max_shift, c->d_lut, c->d_cand_idx,
                          c->d_cand_cell, c->n_cand, c->n_cells, c->cfg.half_w, c->cfg.half_h, c->cfg.px_per_m, d_cell,
                          (long long *)d_highest, d_xy, d_classes, (cudaStream_t)stream));
+    return AT_OK;
+}
+
+// ------------------------------------------------------------------ GCC-PHAT variant (crossover study)
+extern "C" int at_gccphat_device(at_context *c, const uint8_t *d_adc, const int32_t *d_heads, size_t n_frames,
+                                 int32_t *d_lags, float *d_peak, void *stream)
+{
+    if (!c || !d_adc || !d_lags) return fail(AT_EINVAL, "at_gccphat_device: null argument");
+    if (c->cfg.n_bits != 10 && c->cfg.n_bits != 12) return fail(AT_EINVAL, "GCC-PHAT variant: 1024- or 4096-sample frames only");
+    CU(cudaSetDevice(c->cfg.device));
+    const size_t M = c->cfg.n_mics, N = c->n_samples, P = c->n_pairs;
+    const size_t per_frame = M * (N + 1) * sizeof(float2);
+    size_t chunk = ((size_t)128 << 20) / per_frame;
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_frames) chunk = n_frames;
+    if (c->spec_frames < chunk) {
+        if (c->d_spec) { CU(cudaStreamSynchronize((cudaStream_t)stream)); cudaFree(c->d_spec); c->d_spec = nullptr; }
+        CU(cudaMalloc(&c->d_spec, chunk * per_frame));
+        c->spec_frames = chunk;
+    }
+    for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
+        const size_t n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        const cudaError_t e = at_launch_gccphat((int)M, c->cfg.n_bits, c->cfg.max_shift, d_adc + f0 * M * N,
+                                                d_heads ? d_heads + f0 : nullptr, c->d_window, n, c->d_spec, d_lags + f0 * P,
+                                                d_peak ? d_peak + f0 * P : nullptr, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(AT_ECUDA, "GCC-PHAT kernels: %s", cudaGetErrorString(e));
+    }
     return AT_OK;
 }
 

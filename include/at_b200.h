@@ -203,6 +203,13 @@ int at_average_device(at_context *ctx, int64_t *d_est, int32_t *d_est_best, uint
 int at_heatmap_device(at_context *ctx, const int64_t *d_corr /*[A][pairs][2L+1]*/, size_t n_arrays,
                       int32_t *d_cell, int64_t *d_highest, float *d_xy, uint8_t *d_classes, void *stream);
 
+/* GCC-PHAT / FFT variant of the TDOA stage (hand-written radix-2 FFT, no cuFFT), for the direct-vs-FFT crossover
+ * study of long frames / wide lag ranges.  NOT a reference algorithm (the reference correlates directly,
+ * components/correlations.c:9-24): PHAT whitening changes the statistic, only arg-max lags are comparable.
+ * Same integer frame preparation, then float32.  d_peak (optional): normalised peak value per pair. */
+int at_gccphat_device(at_context *ctx, const uint8_t *d_adc, const int32_t *d_heads, size_t n_frames,
+                      int32_t *d_lags /*[F][pairs]*/, float *d_peak /*[F][pairs] or NULL*/, void *stream);
+
 /* Streaming front end (ref: components/rolling_buffer.c:16-41, :73-85; capture loop sample_compute.h:55-99) for
  * n_arrays independent arrays whose ring state lives on the device.  at_stream_push() consumes n_ticks sample triples
  * per array (n_ticks a multiple of 16, <= frame length, so at most one onset per call) and reports per array the
