@@ -141,7 +141,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
                              "sample": "%d frames/step, %s; reference objects -O3 x86-64-v3, one pthread per core" % (per_step, how)},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -164,42 +164,51 @@ def run_ours(args):
     lo, hi = frame_range(rank, world, world * F)
     assert hi - lo == F
     adc, _, _ = loc.synth_device(F, flags=4 if rank == 0 else 0, first_frame=lo)
-    out = {}
+    outs = [{}, {}]            # double-buffered results: the gather of step i overlaps the kernel of step i+1
+    out = outs[0]
     gathered = None
+    comm = torch.cuda.Stream(dev) if world > 1 else None
     if world > 1 and rank == 0:
         gathered = [torch.empty((F, 3), dtype=torch.int32, device=dev) for _ in range(world)]
 
-    def step():
-        loc.localize_device(adc, None, want=WANT, out=out)
-        if world > 1:   # the only bytes that cross NVLink: 12 B of lags per frame to rank 0
-            dist.gather(out["lags"], gathered, dst=0)
+    def step(i):
+        o = outs[i & 1]
+        loc.localize_device(adc, None, want=WANT, out=o)
+        if world > 1:   # the only bytes that cross NVLink: 12 B of lags per frame to rank 0, on a side stream
+            ready = torch.cuda.Event()
+            ready.record(stream)
+            comm.wait_event(ready)
+            with torch.cuda.stream(comm):
+                dist.gather(o["lags"], gathered, dst=0)
 
     def barrier():
+        if comm is not None:
+            stream.wait_stream(comm)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for i in range(max(args.warmup, 3)):
+        step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = loc.kernel_launches()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ev[0].record(stream)
+    ev0.record(stream)
     for i in range(args.steps):
         kev[i][0].record(stream)
-        loc.localize_device(adc, None, want=WANT, out=out)
-        kev[i][1].record(stream)
-        if world > 1:
-            dist.gather(out["lags"], gathered, dst=0)
-        ev[i + 1].record(stream)
+        step(i)
+        kev[i][1].record(stream)          # main stream: brackets the localization kernel only
+    if comm is not None:
+        stream.wait_stream(comm)          # the last gather is inside the timed region
+    ev1.record(stream)
     barrier()
     launches = loc.kernel_launches() - launches0
     clocks = sampler.finish()
-    total_ms = ev[0].elapsed_time(ev[-1])
+    total_ms = ev0.elapsed_time(ev1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -314,13 +323,31 @@ def run_ours(args):
                                           % (n, cores, max(1024, n // cores) / dt1),
                                 "lag_mismatches_vs_gpu": mism}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries (NCCL prints "NCCL version ..." to stdout) must not pollute the one-line contract: route fd 1 to
+    # stderr for the whole run and keep the original stdout for emit().
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
