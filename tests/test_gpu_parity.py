@@ -311,6 +311,40 @@ def test_edge_cases(loc):
     assert loc.kernel_launches() == before + 1
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_ragged_small_batches(kernel, oracle):
+    """Batch sizes around the warp / CTA granularity of the kernels (1..9, 127..130 frames), every frame checked."""
+    loc = make_loc(kernel)
+    adc_all, heads_all, _ = loc.synth_device(130, flags=2 | 4, seed=5)
+    torch = _torch()
+    o = oracle.localize(adc_all.cpu().numpy(), heads=heads_all.cpu().numpy(), want_corr=False)
+    for F in (1, 2, 3, 4, 5, 7, 8, 9, 127, 128, 129, 130):
+        r = loc.localize_device(adc_all[:F].contiguous(), heads_all[:F].contiguous(), want=("lags", "cell", "highest"))
+        torch.cuda.synchronize()
+        assert (r["lags"].cpu().numpy() == o["lags"][:F]).all(), F
+        assert (r["cell"].cpu().numpy() == o["cell"][:F]).all() and (r["highest"].cpu().numpy() == o["highest"][:F]).all(), F
+
+
+def test_bounded_search_paths_are_exercised(loc, oracle):
+    """The likelihood search must take all three routes (first box / widened box / full scan) on suitable data and
+    still equal the oracle's full scan: clean bursts, heavy-noise frames, and flat frames."""
+    torch = _torch()
+    rng = np.random.default_rng(17)
+    clean, _ = burst_frames(256, seed=3)
+    noisy = rng.integers(0, 256, (256, 3, N), dtype=np.uint8)                      # white noise: inconsistent peaks
+    weak, _ = burst_frames(256, seed=4)
+    weak = np.clip(128 + (weak.astype(int) - 128) // 6 + rng.integers(-6, 7, weak.shape), 0, 255).astype(np.uint8)
+    flat = np.full((64, 3, N), 77, np.uint8)
+    adc = np.concatenate([clean, noisy, weak, flat])
+    d = torch.from_numpy(adc).cuda()
+    r = loc.localize_device(d, want=("lags", "cell", "highest", "stats"))
+    torch.cuda.synchronize()
+    o = oracle.localize(adc, want_corr=False, nthreads=8)
+    assert (r["cell"].cpu().numpy() == o["cell"]).all() and (r["highest"].cpu().numpy() == o["highest"]).all()
+    st = r["stats"].cpu().numpy()
+    assert st.sum() == adc.shape[0] and st[0] > 0 and st[2] > 0, st            # first box and full scan both used
+
+
 # ---------------------------------------------------------------- other shapes (no reference pin)
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("shape", [(8, 12, 46, 24), (3, 10, 44, 64), (4, 10, 46, 64), (3, 12, 46, 32), (8, 10, 46, 48)])
