@@ -252,7 +252,7 @@ def run_ours(args):
     kernel_used = args.kernel
     ubench = {}
     if rank == 0:
-        for name in ("imma_s8", "imad_wide", "dp2a", "lds"):
+        for name in ("imma_s8", "imad_wide", "imad", "dp2a", "lds"):
             try:
                 g, mhz = loc.microbench(name)
                 ubench[name] = {"gops": g}
@@ -289,6 +289,12 @@ def run_ours(args):
                 "frac": achieved / peak if peak else None, "traffic": traffic,
                 "peak_source": "measured live: at_microbench(%s) on this GPU" % peak_name,
                 "issued_frac": (achieved * 1622016 / per_frame / peak) if (imma and peak) else None,
+                # the same work expressed against the INTEGER-pipe roofline the direct form would have:
+                # 279,210 int16 MAC per frame vs the measured one-instruction-per-MAC rates of this GPU
+                "int16_tmac_per_s": MAC_PER_FRAME * F / (kern_ms * 1e-3) / 1e12,
+                "vs_int_pipe_roofline": {
+                    "imad_32bit_peak": (MAC_PER_FRAME * F / (kern_ms * 1e-3) / 1e9) / ubench["imad"]["gops"] if ubench.get("imad", {}).get("gops") else None,
+                    "mad_wide_chain_peak": (MAC_PER_FRAME * F / (kern_ms * 1e-3) / 1e9) / ubench["imad_wide"]["gops"] if ubench.get("imad_wide", {}).get("gops") else None},
                 "kernel_ms": kern_ms, "algorithmic_mac_per_frame": MAC_PER_FRAME,
                 "hbm_achieved_gbs": hbm_ach, "hbm_peak_gbs": hbm_peak, "hbm_frac": hbm_ach / hbm_peak,
                 "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
