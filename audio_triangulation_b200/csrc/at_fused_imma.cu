@@ -46,11 +46,6 @@ struct ImmaSmem {
     // 16-byte groups: word index of sample i = (((c >> 5) * 4 + w) * 32 + (c & 31)) * 4 + e with
     // c = i / 16, w = (i / 4) & 3, e = i & 3.
     alignas(16) uint32_t win2[G::N];
-    static __device__ __forceinline__ int win_index(int i)
-    {
-        const int c = i >> 4, w = (i >> 2) & 3, e = i & 3;
-        return ((((c >> 5) * 4 + w) * 32) + (c & 31)) * 4 + e;
-    }
     float gauss[2 * L + 1];
     alignas(16) uint8_t plane[WARPS][3][2][G::PLANE]; // [warp][channel][hi, lo]
     // The epilogue's int64 curves (3 x NJ x 8 bytes) reuse the DATA region [PAD, PAD + N) of this
@@ -81,7 +76,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
     // one-time CTA setup: zero every plane (the pads stay zero), doubled window, Gaussian factors
     for (int i = tid; i < (int)(sizeof(s.plane) / 16); i += WARPS * 32)
         reinterpret_cast<uint4 *>(&s.plane[0][0][0][0])[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < N; i += WARPS * 32) s.win2[S::win_index(i)] = (uint32_t)(2 * (int)p.window[i]) << ((i & 1) * 16);
+    imma_win_fill(s.win2, p.window, N, tid, WARPS * 32);
     for (int i = tid; i < 2 * L + 1; i += WARPS * 32) s.gauss[i] = p.gauss[i];
     __syncthreads();
 
@@ -122,9 +117,6 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
         //      (int16)((b - mean) << 8) = 256 * sext8(b - mean);  ((256 a) * W) >> 15 = (a * 2W) >> 8
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
-            // per-byte x - mean (mod 256) = x + k with k = 256 - mean: add the low 7 bits, xor the top bits
-            const uint32_t k4 = (uint32_t)((256 - mean[ch]) & 0xFF) * 0x01010101u;
-            const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
 #pragma unroll
             for (int q = 0; q < Q; q++) {
                 const int j0 = q * 512 + lane * 16;                   // ring slot of this lane's 16 bytes
@@ -133,28 +125,14 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                 if ((head & 15) == 0) {
                     const int i0 = (j0 - head) & (N - 1);             // chronological index, 16-aligned
                     uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int w4 = 0; w4 < 4; w4++) {
-                        const uint4 ww = *reinterpret_cast<const uint4 *>(&s.win2[S::win_index(i0 + 4 * w4)]);
-                        const uint32_t d = sub_bytes(rw[w4], k7, kM);   // (b - mean) mod 256, per byte
-                        // IDP.2A does byte extraction, sign extension and the multiply in one instruction:
-                        // (u16 pair) . (s8 pair) with one u16 zero selects a single signed byte of d
-                        const int p0 = dp2a_lo_u16s8(ww.x, d), p1 = dp2a_lo_u16s8(ww.y, d);
-                        const int p2 = dp2a_hi_u16s8(ww.z, d), p3 = dp2a_hi_u16s8(ww.w, d);
-                        // prepared sample = bits 8..23 of the product: low byte = byte 1, high byte = byte 2
-                        const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
-                        const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
-                        lo[w4] = __byte_perm(t01, t23, 0x5410);
-                        hi[w4] = __byte_perm(t01, t23, 0x7632);
-                    }
+                    imma_prep16(rw, mean[ch], s.win2, i0, hi, lo);
                     *reinterpret_cast<uint4 *>(plane(ch, 0) + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4 *>(plane(ch, 1) + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 } else {   // ring head not 16-aligned: scalar stores (rare; capture heads are arbitrary)
 #pragma unroll
                     for (int e = 0; e < 16; e++) {
                         const int i = (j0 + e - head) & (N - 1);
-                        const int a = (int)(signed char)(((rw[e >> 2] >> (8 * (e & 3))) - (uint32_t)mean[ch]) & 0xFFu);
-                        const int pr = a * (int)(s.win2[S::win_index(i)] >> ((i & 1) * 16));
+                        const int pr = imma_prep1(rw[e >> 2] >> (8 * (e & 3)), mean[ch], s.win2, i);
                         plane(ch, 0)[PAD + i] = (uint8_t)(pr >> 16);
                         plane(ch, 1)[PAD + i] = (uint8_t)(pr >> 8);
                     }

@@ -53,11 +53,6 @@ struct Imma3Smem {
     alignas(16) uint32_t win2[G::N];                 // pre-masked 2*W, chunk-interleaved (see at_fused_imma.cu)
     float gauss[2 * L + 1];
     alignas(128) uint8_t slice[WARPS][G::SLICE];
-    static __device__ __forceinline__ int win_index(int i)
-    {
-        const int c = i >> 4, w = (i >> 2) & 3, e = i & 3;
-        return ((((c >> 5) * 4 + w) * 32) + (c & 31)) * 4 + e;
-    }
 };
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&a)[4], uint32_t smem_addr)
@@ -86,7 +81,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma3_kernel
     // one-time CTA setup: zero every slice (pads stay zero), window, Gaussian factors
     for (int i = tid; i < (int)(sizeof(s.slice) / 16); i += WARPS * 32)
         reinterpret_cast<uint4 *>(&s.slice[0][0])[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < N; i += WARPS * 32) s.win2[S::win_index(i)] = (uint32_t)(2 * (int)p.window[i]) << ((i & 1) * 16);
+    imma_win_fill(s.win2, p.window, N, tid, WARPS * 32);
     for (int i = tid; i < 2 * L + 1; i += WARPS * 32) s.gauss[i] = p.gauss[i];
     __syncthreads();
 
@@ -129,8 +124,6 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma3_kernel
         if ((head & 15) == 0) {
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-                const uint32_t k4 = (uint32_t)((256 - mean[ch]) & 0xFF) * 0x01010101u;
-                const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
                 uint32_t carry_hi = 0, carry_lo = 0;          // last word of the previous chunk (lane 31), for lane 0
 #pragma unroll
                 for (int q = 0; q < 2; q++) {
@@ -139,17 +132,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma3_kernel
                     const uint4 v = raw[ch * 2 + q];
                     const uint32_t rw[4] = {v.x, v.y, v.z, v.w};
                     uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int w4 = 0; w4 < 4; w4++) {
-                        const uint4 ww = *reinterpret_cast<const uint4 *>(&s.win2[S::win_index(i0 + 4 * w4)]);
-                        const uint32_t d = sub_bytes(rw[w4], k7, kM);
-                        const int p0 = dp2a_lo_u16s8(ww.x, d), p1 = dp2a_lo_u16s8(ww.y, d);
-                        const int p2 = dp2a_hi_u16s8(ww.z, d), p3 = dp2a_hi_u16s8(ww.w, d);
-                        const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
-                        const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
-                        lo[w4] = __byte_perm(t01, t23, 0x5410);
-                        hi[w4] = __byte_perm(t01, t23, 0x7632);
-                    }
+                    imma_prep16(rw, mean[ch], s.win2, i0, hi, lo);
                     uint8_t *const at = sl + PAD + i0;           // plane-relative position of this chunk
                     if (ch < 2) {       // x side (a, b): copies delayed by 0..3 bytes
                         // chronological predecessor word: lane-1's last word; for the first chunk of the frame: zero
@@ -217,8 +200,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma3_kernel
                     const uint32_t rw[4] = {v.x, v.y, v.z, v.w};
                     for (int e = 0; e < 16; e++) {
                         const int i = (q * 512 + lane * 16 + e - head) & (N - 1);
-                        const int a = (int)(signed char)(((rw[e >> 2] >> (8 * (e & 3))) - (uint32_t)mean[ch]) & 0xFFu);
-                        const int pr = a * (int)(s.win2[S::win_index(i)] >> ((i & 1) * 16));
+                        const int pr = imma_prep1(rw[e >> 2] >> (8 * (e & 3)), mean[ch], s.win2, i);
                         const uint8_t bh = (uint8_t)(pr >> 16), bl = (uint8_t)(pr >> 8);
                         if (ch < 2)
                             for (int c = 0; c < 4; c++) { sl[G::XC(2 * ch, c) + PAD + i + c] = bh; sl[G::XC(2 * ch + 1, c) + PAD + i + c] = bl; }

@@ -33,11 +33,6 @@ struct CtaSmem {
     EpiSmem<NMICS, NBITS, L> epi;
     float gauss[2 * L + 1];
     int mean[NMICS];
-    static __device__ __forceinline__ int win_index(int i)
-    {
-        const int c = i >> 4, w = (i >> 2) & 3, e = i & 3;
-        return ((((c >> 5) * 4 + w) * 32) + (c & 31)) * 4 + e;
-    }
 };
 
 __device__ __forceinline__ uint32_t cta_lds32(uint32_t smem_addr)
@@ -107,7 +102,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_cta_ker
 
     for (int i = tid; i < (int)(sizeof(s.plane) / 16); i += THREADS)
         reinterpret_cast<uint4 *>(&s.plane[0][0][0])[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < N; i += THREADS) s.win2[S::win_index(i)] = (uint32_t)(2 * (int)p.window[i]) << ((i & 1) * 16);
+    imma_win_fill(s.win2, p.window, N, tid, THREADS);
     for (int i = tid; i < 2 * L + 1; i += THREADS) s.gauss[i] = p.gauss[i];
     __syncthreads();
     const uint32_t planes_s = smem_u32(&s.plane[0][0][0]);
@@ -135,27 +130,14 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_cta_ker
             const int mean = s.mean[ch];
             if ((head & 15) == 0) {
                 const int i0 = (j0 - head) & (N - 1);
-                const uint32_t k4 = (uint32_t)((256 - mean) & 0xFF) * 0x01010101u;
-                const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
                 uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int w4 = 0; w4 < 4; w4++) {
-                    const uint4 ww = *reinterpret_cast<const uint4 *>(&s.win2[S::win_index(i0 + 4 * w4)]);
-                    const uint32_t d = sub_bytes(rw[w4], k7, kM);
-                    const int p0 = dp2a_lo_u16s8(ww.x, d), p1 = dp2a_lo_u16s8(ww.y, d);
-                    const int p2 = dp2a_hi_u16s8(ww.z, d), p3 = dp2a_hi_u16s8(ww.w, d);
-                    const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
-                    const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
-                    lo[w4] = __byte_perm(t01, t23, 0x5410);
-                    hi[w4] = __byte_perm(t01, t23, 0x7632);
-                }
+                imma_prep16(rw, mean, s.win2, i0, hi, lo);
                 *reinterpret_cast<uint4 *>(&s.plane[ch][0][PAD + i0]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(&s.plane[ch][1][PAD + i0]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             } else {
                 for (int e = 0; e < 16; e++) {
                     const int i = (j0 + e - head) & (N - 1);
-                    const int a = (int)(signed char)(((rw[e >> 2] >> (8 * (e & 3))) - (uint32_t)mean) & 0xFFu);
-                    const int pr = a * (int)(s.win2[S::win_index(i)] >> ((i & 1) * 16));
+                    const int pr = imma_prep1(rw[e >> 2] >> (8 * (e & 3)), mean, s.win2, i);
                     s.plane[ch][0][PAD + i] = (uint8_t)(pr >> 16);
                     s.plane[ch][1][PAD + i] = (uint8_t)(pr >> 8);
                 }

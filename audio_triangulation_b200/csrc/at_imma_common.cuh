@@ -62,6 +62,49 @@ __device__ __forceinline__ uint32_t sub_bytes(uint32_t x, uint32_t k7, uint32_t 
     return t ^ (x & 0x80808080u) ^ kM;
 }
 
+// ---------------------------------------------------------------- frame preparation shared by the tensor kernels
+// The doubled window 2*W[i] ((a * 2W) >> 8 == (a * W) >> 7, so the prepared sample's low/high bytes are bytes 1/2 of
+// the product) is kept in shared memory one 32-bit word per sample, pre-masked for IDP.2A (even samples in the low
+// half, odd samples in the high half) and chunk-interleaved so that lanes working on consecutive 16-sample chunks read
+// consecutive 16-byte groups (conflict-free LDS.128).
+__device__ __forceinline__ int imma_win_index(int i)
+{
+    const int c = i >> 4, w = (i >> 2) & 3, e = i & 3;
+    return ((((c >> 5) * 4 + w) * 32) + (c & 31)) * 4 + e;
+}
+__device__ __forceinline__ void imma_win_fill(uint32_t *win2, const int16_t *window, int n, int tid, int nthreads)
+{
+    for (int i = tid; i < n; i += nthreads) win2[imma_win_index(i)] = (uint32_t)(2 * (int)window[i]) << ((i & 1) * 16);
+}
+// 16 consecutive samples (chronological index i0, 16-aligned): raw ADC bytes rw[4] -> hi / lo byte-plane words.
+// ref: rolling_buffer.c:66 (x - mean), buffer.c:16 (<<8 wraps to 256 * sext8), buffer.c:8-9 (Q15 window).
+__device__ __forceinline__ void imma_prep16(const uint32_t (&rw)[4], int mean, const uint32_t *win2, int i0,
+                                            uint32_t (&hi)[4], uint32_t (&lo)[4])
+{
+    // per-byte x - mean (mod 256) = x + k with k = 256 - mean: add the low 7 bits, xor the top bits
+    const uint32_t k4 = (uint32_t)((256 - mean) & 0xFF) * 0x01010101u;
+    const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
+#pragma unroll
+    for (int w4 = 0; w4 < 4; w4++) {
+        const uint4 ww = *reinterpret_cast<const uint4 *>(&win2[imma_win_index(i0 + 4 * w4)]);
+        const uint32_t d = sub_bytes(rw[w4], k7, kM);
+        // IDP.2A does byte extraction, sign extension and the multiply in one instruction:
+        // (u16 pair) . (s8 pair) with one u16 zero selects a single signed byte of d
+        const int p0 = dp2a_lo_u16s8(ww.x, d), p1 = dp2a_lo_u16s8(ww.y, d);
+        const int p2 = dp2a_hi_u16s8(ww.z, d), p3 = dp2a_hi_u16s8(ww.w, d);
+        const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
+        const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
+        lo[w4] = __byte_perm(t01, t23, 0x5410);
+        hi[w4] = __byte_perm(t01, t23, 0x7632);
+    }
+}
+// one sample (unaligned ring heads): returns the 24-bit product whose bytes 2 / 1 are the high / low plane bytes
+__device__ __forceinline__ int imma_prep1(uint32_t raw_byte, int mean, const uint32_t *win2, int i)
+{
+    const int a = (int)(signed char)((raw_byte - (uint32_t)mean) & 0xFFu);
+    return a * (int)(win2[imma_win_index(i)] >> ((i & 1) * 16));
+}
+
 // 64-bit maximum across the warp with two REDUX instructions (high word signed, low word unsigned).
 __device__ __forceinline__ long long warp_max_i64(long long key)
 {
