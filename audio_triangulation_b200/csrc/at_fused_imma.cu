@@ -265,6 +265,6 @@ cudaError_t at_launch_fused_imma(const AtShape &sh, const AtFusedParams &p, int 
         return ctas == 5 ? atk::launch_imma<10, 46, 4, 5>(p, sm_count, st) : atk::launch_imma<10, 46, 4, 4>(p, sm_count, st);
     }
     if (sh.n_bits == 10 && sh.max_shift == 44) return atk::launch_imma<10, 44, 4, 4>(p, sm_count, st);
-    if (sh.n_bits == 12 && sh.max_shift == 46) return atk::launch_imma<12, 46, 4, 1>(p, sm_count, st);
+    if (sh.n_bits == 12 && sh.max_shift == 46) return atk::launch_imma<12, 46, 7, 1>(p, sm_count, st);   // 7 warps x 25.5 KB of planes fill the SM
     return cudaErrorInvalidValue;
 }
