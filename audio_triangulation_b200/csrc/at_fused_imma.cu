@@ -14,11 +14,13 @@
 // reference's int64 accumulation.
 //
 // Mapping: ONE WARP PER FRAME.  A warp loads its frame (coalesced 16-byte global loads), removes
-// DC, applies <<8 and the window, writes hi/lo byte planes of the three channels to its private
-// shared-memory slice, runs 33 k-steps x 12 IMMA (3 pairs x {hh, hl, lh, ll}) with fragments
-// loaded straight from the planes (A: aligned 8-byte loads, the Hankel rows overlap in memory;
-// B: aligned 4-byte loads + funnel shift for the per-column byte offset), then finds the three
-// arg-max lags with warp shuffles.  No block-level synchronisation after start-up.
+// DC, applies <<8 and the window (imma_prep16), writes hi/lo byte planes of the three channels to
+// its private shared-memory slice, runs 33 k-steps x 12 IMMA (3 pairs x {hh, hl, lh, ll}) with
+// fragments loaded straight from the planes (A: four 32-bit loads per plane, the Hankel rows overlap
+// in memory and nothing is materialised; B: three aligned 32-bit loads + two funnel shifts for the
+// per-column byte offset), then finds the three first-max lags with REDUX reductions and, if asked,
+// runs the warp-scope epilogue (Gaussian re-weighting, bounded likelihood search).  No block-level
+// synchronisation after start-up.  Why the loop looks the way it does: DESIGN.md section 4.1.
 #include <limits.h>
 #include <stdlib.h>
 
@@ -40,11 +42,7 @@ struct ImmaGeo {
 template <int NBITS, int L, int WARPS>
 struct ImmaSmem {
     using G = ImmaGeo<NBITS, L>;
-    // 2 * W[i] ((a * 2W) >> 8 == (a * W) >> 7, byte aligned), one 32-bit word per sample already masked
-    // for IDP.2A: even samples hold 2W in the low half, odd samples in the high half, other half zero.
-    // Stored chunk-interleaved so the lanes of a warp (consecutive 16-sample chunks) read consecutive
-    // 16-byte groups: word index of sample i = (((c >> 5) * 4 + w) * 32 + (c & 31)) * 4 + e with
-    // c = i / 16, w = (i / 4) & 3, e = i & 3.
+    // doubled, pre-masked, chunk-interleaved window (layout: imma_win_index in at_imma_common.cuh)
     alignas(16) uint32_t win2[G::N];
     float gauss[2 * L + 1];
     alignas(16) uint8_t plane[WARPS][3][2][G::PLANE]; // [warp][channel][hi, lo]

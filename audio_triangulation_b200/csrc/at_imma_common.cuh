@@ -31,16 +31,6 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t *p)
     return r;
 }
 
-// Sign-extend one byte of a word with a single PRMT (selector nibble 8+e = "replicate the sign of
-// byte e").  Raw PTX: __byte_perm() is specified to ignore bit 3 of each nibble and nvcc masks it.
-template <int SEL>
-__device__ __forceinline__ int sext_byte(uint32_t w)
-{
-    int r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "n"(SEL));
-    return r;
-}
-
 // a = two unsigned 16-bit halves, b = four signed bytes: a.lo*b0 + a.hi*b1 (lo) / a.lo*b2 + a.hi*b3 (hi)
 __device__ __forceinline__ int dp2a_lo_u16s8(uint32_t a, uint32_t b)
 {
