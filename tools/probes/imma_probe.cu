@@ -85,6 +85,19 @@ __global__ void __launch_bounds__(128) probe(int iters, int seed, int *sink)
                 for (int k = 0; k < 24; k++) asm volatile("prmt.b32 %0, %1, %2, 0x3210;" : "=r"(x[k & 7]) : "r"(x[(k + 1) & 7]), "r"(it));
             }
         }
+        if (MODE == 13) {    // 48 x m8n8k16 (same MACs as 12 x m16n8k32)
+#pragma unroll
+            for (int i = 0; i < 48; i++)
+                asm volatile("mma.sync.aligned.m8n8k16.row.col.s32.s8.s8.s32 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+r"(c[i % 12][(i / 12) & 1]), "+r"(c[i % 12][2 + ((i / 12) & 1)]) : "r"(A[i & 3][i & 3]), "r"(B[i & 3][i & 1]));
+        }
+        if (MODE == 14) {    // 24 x m16n8k16 (same MACs as 12 x m16n8k32)
+#pragma unroll
+            for (int i = 0; i < 24; i++)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                             : "+r"(c[i % 12][0]), "+r"(c[i % 12][1]), "+r"(c[i % 12][2]), "+r"(c[i % 12][3])
+                             : "r"(A[i & 3][0]), "r"(A[i & 3][1]), "r"(B[i & 3][i & 1]));
+        }
         // operands change every iteration, like freshly loaded fragments
         A[it & 3][it & 3] += it; B[(it + 1) & 3][it & 1] ^= it;
     }
@@ -135,6 +148,8 @@ int main()
         run<10>("kernel pattern + 12 LDS.64", w, sms);
         run<11>("kernel pattern + 6 LDS.128", w, sms);
         run<12>("kernel pattern + 24 PRMT", w, sms);
+        run<13>("48 x m8n8k16 (= MACs of 12 x m16n8k32; per 12-group)", w, sms);
+        run<14>("24 x m16n8k16 (= MACs of 12 x m16n8k32; per 12-group)", w, sms);
     }
     return 0;
 }
