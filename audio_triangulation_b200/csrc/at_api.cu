@@ -75,6 +75,7 @@ struct at_context {
     // device tables
     float *d_mic_xy = nullptr; uint8_t *d_lut = nullptr; uint8_t *d_cand_idx = nullptr; int32_t *d_cand_cell = nullptr;
     uint8_t *d_cs_idx = nullptr; int32_t *d_cs_cell = nullptr; int32_t *d_cs_grid = nullptr; float2 *d_cell_xy = nullptr;
+    int4 *d_peak_tab = nullptr;
     int16_t *d_window = nullptr; float *d_gauss = nullptr; int32_t *d_delay_q8 = nullptr;
     // host copies
     std::vector<float> h_mic_xy; std::vector<uint8_t> h_lut; std::vector<int32_t> h_delay_q8;
@@ -124,7 +125,7 @@ extern "C" void at_destroy(at_context *c)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
-                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec};
+                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_peak_tab};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -211,6 +212,22 @@ static int create_impl(const at_config *cfg, at_context *c)
         CU(cudaMemcpy(c->d_cs_idx, cs_idx.data(), cs_idx.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_cs_cell, cs_cell.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_cs_grid, grid.data(), sizeof(int32_t) * grid.size(), cudaMemcpyHostToDevice));
+        // 3 pairs: direct table over the whole (i0, i1, i2) cube -> first cell of that tuple and its plane
+        // coordinates, so that a frame whose three peaks form a tuple of the LUT is settled by one load
+        // (index bookkeeping only; 16 bytes x NL^3 = 12.9 MB at NL = 93, only the ~2.5 k present tuples are ever hot)
+        if (P == 3) {
+            std::vector<float2> xy((size_t)c->n_cells);
+            CU(cudaMemcpy(xy.data(), c->d_cell_xy, sizeof(float2) * xy.size(), cudaMemcpyDeviceToHost));
+            std::vector<int4> tab((size_t)NLg * NLg * NLg, make_int4(-1, 0, 0, 0));
+            for (int t = 0; t < T; t++) {
+                const size_t at = ((size_t)(uint8_t)keys[t][0] * NLg + (uint8_t)keys[t][1]) * NLg + (uint8_t)keys[t][2];
+                int xb, yb;
+                memcpy(&xb, &xy[first_cell[t]].x, 4); memcpy(&yb, &xy[first_cell[t]].y, 4);
+                tab[at] = make_int4(first_cell[t], xb, yb, 0);
+            }
+            CU(cudaMalloc(&c->d_peak_tab, sizeof(int4) * tab.size()));
+            CU(cudaMemcpy(c->d_peak_tab, tab.data(), sizeof(int4) * tab.size(), cudaMemcpyHostToDevice));
+        }
     }
 
     // window table for this frame length
@@ -300,7 +317,7 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
 {
     p.window = c->d_window; p.gauss = c->d_gauss; p.lut = c->d_lut;
     p.cand_idx = c->d_cand_idx; p.cand_cell = c->d_cand_cell;
-    p.cs_idx = c->d_cs_idx; p.cs_cell = c->d_cs_cell; p.cs_grid = c->d_cs_grid;
+    p.cs_idx = c->d_cs_idx; p.cs_cell = c->d_cs_cell; p.cs_grid = c->d_cs_grid; p.peak_tab = c->d_peak_tab;
     p.opaque_four = 4;
     p.cell_xy = c->d_cell_xy;
     static const int dbg = getenv("AT_DEBUG_SKIP") ? atoi(getenv("AT_DEBUG_SKIP")) : 0;   // timing experiments only

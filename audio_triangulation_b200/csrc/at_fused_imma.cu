@@ -60,7 +60,7 @@ __device__ __forceinline__ void load_b(uint32_t (&b)[2], const uint8_t *plane_k0
     b[1] = __funnelshift_r(w1, w2, bsh);
 }
 
-template <int NBITS, int L, int WARPS, int CTAS_PER_SM>
+template <int NBITS, int L, int WARPS, int CTAS_PER_SM, int UNROLL>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(const AtFusedParams p)
 {
     using G = ImmaGeo<NBITS, L>;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
         const uint32_t ya_s = smem_u32(ya);
         const uint32_t ya_4 = ya_s + (uint32_t)p.opaque_four;
         const int nsteps = (p.debug_skip & 2) ? 0 : G::KSTEPS;   // profiling knob, kept out of the loop body
-#pragma unroll 3
+#pragma unroll UNROLL
         for (int ks = 0; ks < nsteps; ks++) {
             const int k0 = 32 * ks;
             uint32_t Y[4][4], Xah[2], Xal[2], Xbh[2], Xbl[2];
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
         // ---- recombine in int64, arg-max per pair (correlations.c:20-23): key = value * 128 + (127 - j),
         //      so the 64-bit maximum is the largest value and, among equals, the lowest lag
         int best3[3];
+        long long peak[3];
 #pragma unroll
         for (int pr = 0; pr < 3; pr++) {
             long long key = LLONG_MIN;
@@ -210,15 +211,27 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
             for (int i = 0; i < 4; i++) {
                 const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
                 const long long v = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i] + (long long)acc[pr][2][i];
-                if (extras && j < G::NJ) curve_base[pr * CSTRIDE + j] = v;
                 const long long k = v * 128 + (127 - j);
                 if (j >= PAD - L && j <= PAD + L && k > key) key = k;
             }
             key = warp_max_i64(key);
             best3[pr] = 127 - (int)(key & 127) - PAD;
+            peak[pr] = key >> 7;
         }
         if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? best3[0] : (lane == 1 ? best3[1] : best3[2]);
-        if (extras) {
+        // position products only (cell / xy / highest / gate): consistent peaks are settled by one table load
+        bool settled = !extras;
+        if (extras && !(p.raw || p.corr || p.classes))
+            settled = peak_tuple_lookup<L>(p, f, lane, best3[0], best3[1], best3[2], peak);
+        if (!settled) {   // whole curves wanted, or peaks that are no LUT tuple: curves to shared memory, warp-scope epilogue
+#pragma unroll
+            for (int pr = 0; pr < 3; pr++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
+                    if (j < G::NJ)
+                        curve_base[pr * CSTRIDE + j] = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i] + (long long)acc[pr][2][i];
+                }
             __syncwarp();
             epilogue_warp<L, PAD, G::NJ, CSTRIDE>(curve_base, best3[0], best3[1], best3[2], s.gauss, p, f, lane);
         }
@@ -226,11 +239,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
     }
 }
 
-template <int NBITS, int L, int WARPS, int CTAS_PER_SM>
+template <int NBITS, int L, int WARPS, int CTAS_PER_SM, int UNROLL = 3>
 static cudaError_t launch_imma(const AtFusedParams &p, int sm_count, cudaStream_t st)
 {
     using S = ImmaSmem<NBITS, L, WARPS>;
-    auto kern = at_fused_imma_kernel<NBITS, L, WARPS, CTAS_PER_SM>;
+    auto kern = at_fused_imma_kernel<NBITS, L, WARPS, CTAS_PER_SM, UNROLL>;
     const int smem = (int)sizeof(S);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -259,8 +272,7 @@ cudaError_t at_launch_fused_imma(const AtShape &sh, const AtFusedParams &p, int 
 {
     if (p.sig16 || sh.n_mics != 3) return cudaErrorInvalidValue;
     if (sh.n_bits == 10 && sh.max_shift == 46) {
-        static const int ctas = getenv("AT_IMMA_CTAS") ? atoi(getenv("AT_IMMA_CTAS")) : 4;   // tuning knob
-        return ctas == 5 ? atk::launch_imma<10, 46, 4, 5>(p, sm_count, st) : atk::launch_imma<10, 46, 4, 4>(p, sm_count, st);
+        return atk::launch_imma<10, 46, 4, 4>(p, sm_count, st);   // k-loop unrolled by 3: 11 and 33 measured 7-12 % slower
     }
     if (sh.n_bits == 10 && sh.max_shift == 44) return atk::launch_imma<10, 44, 4, 4>(p, sm_count, st);
     if (sh.n_bits == 12 && sh.max_shift == 46) return atk::launch_imma<12, 46, 7, 1>(p, sm_count, st);   // 7 warps x 25.5 KB of planes fill the SM

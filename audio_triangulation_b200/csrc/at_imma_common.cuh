@@ -114,6 +114,32 @@ __device__ __forceinline__ Best warp_best_cell(Best x)
     return r;
 }
 
+// Peak-tuple look-up (3-pair arrays): when the three first-max lags (b0, b1, b2) form a tuple of the LUT, that tuple's
+// likelihood is the sum of the three curve maxima and nothing can tie it once every raw peak is >= 2048 (an entry off
+// the peak is <= trunc(fl(peak) * g[1]), g[1] = exp(-1/36) < 0.973, far below trunc(fl(peak))); the tuples are
+// distinct, so the first row-major cell of that tuple is the reference's answer (vga_heatmap.h:96-108).  One 16-byte
+// load settles cell, xy and highest_L without ever materialising the curves.  peak[] = raw curve maxima.
+// Returns false when the frame needs the search of epilogue_warp.
+template <int L>
+__device__ __forceinline__ bool peak_tuple_lookup(const AtFusedParams &p, unsigned long long f, int lane,
+                                                  int b0s, int b1s, int b2s, const long long (&peak)[3])
+{
+    constexpr int NL = 2 * L + 1;
+    if (!p.peak_tab || peak[0] < 2048 || peak[1] < 2048 || peak[2] < 2048) return false;
+    const int4 e = __ldg(&p.peak_tab[((b0s + L) * NL + (b1s + L)) * NL + (b2s + L)]);
+    if (e.x < 0) return false;
+    if (lane == 0) {
+        if (p.cell) p.cell[f] = e.x;
+        if (p.xy) reinterpret_cast<float2 *>(p.xy)[f] = make_float2(__int_as_float(e.y), __int_as_float(e.z));
+        if (p.highest)   // g[0] = 1: the post-Gaussian peak is the float-rounded raw peak (correlations.c:30-31)
+            p.highest[f] = __float2ll_rz(__ll2float_rn(peak[0])) + __float2ll_rz(__ll2float_rn(peak[1])) +
+                           __float2ll_rz(__ll2float_rn(peak[2]));
+        if (p.gate) p.gate[f] = (b0s * b0s + b1s * b1s + b2s * b2s) > 4 ? 1 : 0;   // sample_compute.h:124-134
+        if (p.stats) atomicAdd(&p.stats[3], 1ull);
+    }
+    return true;
+}
+
 // Warp-scope epilogue for the optional products; curve[][] holds raw sums indexed by j = s + PAD,
 // b0..b2 are the three best shifts (warp-uniform).
 template <int L, int PAD, int NJ, int CSTRIDE>
@@ -202,8 +228,28 @@ __device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, in
         auto bound = [&](float pk, int r) -> long long { return r <= 2 * L ? __float2ll_rz(__fmul_rn(pk, gauss_s[r])) : 0; };
         constexpr int R_FIRST = 2, R_MAX = 12;
         int how = 0;
-        b = scan_box(R_FIRST, R_FIRST);
-        bool ok = b.v > bound(pk0, R_FIRST + 1) + others0 && b.v > bound(pk1, R_FIRST + 1) + others1;
+        bool ok = false;
+        // Consistent peaks: if the LUT holds the tuple (best_0, best_1, best_2) itself, its likelihood is the sum of
+        // the three curve maxima.  No other tuple can tie it when every peak is >= 1024: an entry off the peak is
+        // <= trunc(fl(peak) * g[1]) with g[1] = exp(-1/36) < 0.973, at least 27 below trunc(fl(peak)).  The tuples
+        // are distinct, so the hit is unique and cs_cell holds its first row-major cell.
+        if (pmax[0] >= 1024 && pmax[1] >= 1024 && pmax[2] >= 1024) {
+            const int lo = p.cs_grid[b0 * NL + b1], hi = p.cs_grid[b0 * NL + b1 + 1];
+            const int want2 = b2s + L;
+            for (int c0 = lo; c0 < hi && !ok; c0 += 32) {
+                const int c = c0 + lane;
+                const unsigned hit = __ballot_sync(0xffffffffu, c < hi && p.cs_idx[2 * p.n_cand + c] == want2);
+                if (hit) {
+                    b.v = pmax[0] + pmax[1] + pmax[2];
+                    b.i = p.cs_cell[c0 + __ffs(hit) - 1];
+                    ok = true; how = 3;
+                }
+            }
+        }
+        if (!ok) {
+            b = scan_box(R_FIRST, R_FIRST);
+            ok = b.v > bound(pk0, R_FIRST + 1) + others0 && b.v > bound(pk1, R_FIRST + 1) + others1;
+        }
         if (!ok && b.v != LLONG_MIN) {          // widen: smallest radii whose outside bound is below what we hold
             int r0 = -1, r1 = -1;
             for (int r = R_FIRST; r <= R_MAX && (r0 < 0 || r1 < 0); r++) {

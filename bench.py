@@ -223,7 +223,8 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         st = st.cpu().numpy().astype(float)
         if st.sum() > 0:
-            search = {"first_box": st[0] / st.sum(), "widened_box": st[1] / st.sum(), "full_scan": st[2] / st.sum()}
+            search = {"peak_tuple_lookup": st[3] / st.sum(), "first_box": st[0] / st.sum(), "widened_box": st[1] / st.sum(),
+                      "full_scan": st[2] / st.sum()}
     except Exception:
         pass
 

@@ -326,7 +326,7 @@ def test_ragged_small_batches(kernel, oracle):
 
 
 def test_bounded_search_paths_are_exercised(loc, oracle):
-    """The likelihood search must take all three routes (first box / widened box / full scan) on suitable data and
+    """The likelihood search must take its routes (peak-tuple look-up / first box / widened box / full scan) on suitable data and
     still equal the oracle's full scan: clean bursts, heavy-noise frames, and flat frames."""
     torch = _torch()
     rng = np.random.default_rng(17)
@@ -342,7 +342,7 @@ def test_bounded_search_paths_are_exercised(loc, oracle):
     o = oracle.localize(adc, want_corr=False, nthreads=8)
     assert (r["cell"].cpu().numpy() == o["cell"]).all() and (r["highest"].cpu().numpy() == o["highest"]).all()
     st = r["stats"].cpu().numpy()
-    assert st.sum() == adc.shape[0] and st[0] > 0 and st[2] > 0, st            # first box and full scan both used
+    assert st.sum() == adc.shape[0] and st[3] > 0 and st[2] > 0 and st[0] + st[1] > 0, st   # look-up, a bounded box and the full scan all used
 
 
 # ---------------------------------------------------------------- other shapes (no reference pin)
