@@ -1,0 +1,397 @@
+// at_fused_umma.cu -- fused localization kernel on the 5th-generation tensor cores (tcgen05 / UMMA), AT_KERNEL_UMMA.
+//
+// Polyphase form of the lagged cross-correlation (ref: components/correlations.c:9-18,
+//     corr[s] = sum_i x[i] * y[i+s]).  Split time as i = 16 q + phi.  With Y the zero-padded y frame
+// (sample i at Y[PAD + i]) the int8 matrix product
+//     D[m][phi] = sum_q Y[m + 16 q] * x[phi + 16 q]            m = 0..127, phi = 0..15, q = 0..63
+// holds, on its diagonals, every term of the correlation:  corr[s] = sum_phi D[s + PAD + phi][phi].
+// Both operands are the PLAIN byte planes in shared memory, read as MN-major UMMA operands without swizzle:
+//     A[m][q] = Y[m + 16 q]  is a Hankel matrix -- MN chunks 16 bytes apart (SBO = 16 B), K rows 16 bytes apart, so
+//                            the chunks overlap in memory and nothing is materialised;
+//     B[n][q] = x[n + 16 q]  is the polyphase matrix of x; several planes sit side by side (SBO = plane stride).
+// One tcgen05.mma kind::i8 (K = 32) covers 512 samples, so a frame needs 2 K-steps instead of 33 mma.sync steps.
+// (tools/probes/umma_probe.cu is the stand-alone proof of this operand trick.)
+//
+// int16 samples are split into balanced signed digits w = 256 h + l, h and l both in [-128, 127] (possible because
+// the windowed samples stay inside [-32767, 32511]); corr = 65536 (h.h) + 256 (h.l + l.h) + (l.l) as in the
+// mma.sync kernel, each class in its own 16 TMEM columns, int32 (|sum| < 2^26), recombined in int64: bit-exact.
+//
+// The diagonal sums are the CUDA cores' job.  To halve them every plane is stored twice, the second copy advanced by
+// 8 bytes, and both copies are accumulated into the same tile:  D2[m][phi] = D[m][phi] + D[m+8][phi+8]  for
+// phi = 0..7, i.e. two entries of the same diagonal; corr[s] = sum_{phi<8} D2[s + PAD + phi][phi].
+//
+// CTA = 16 warps, one CTA per SM, persistent:
+//   warps 0-3   prep: one frame each -- coalesced 16-byte loads, DC removal, <<8, window (as imma_prep16), digit
+//               planes to shared memory (both copies), then ONE lane issues the frame's 27 MMAs and commits them to
+//               two mbarriers (accumulators ready / planes free);
+//   warps 4-15  three epilogue sets of four warps, set k bound to TMEM slot k (144 columns): TMEM -> registers
+//               (warp w reads lane quadrant w % 4), transposing scatter through shared memory, diagonal sums,
+//               int64 recombination, first-max arg-max (correlations.c:20-23), then peak-tuple look-up or the
+//               warp-scope epilogue of at_imma_common.cuh for everything else.
+#include <limits.h>
+#include <stdlib.h>
+
+#include "at_imma_common.cuh"
+
+namespace atk {
+
+template <int L>
+struct UmmaGeo {
+    static constexpr int N = 1024, NBITS = 10;
+    static constexpr int PAD = 48;                      // lag index j = s + PAD; also the left zero pad of a plane
+    static constexpr int PLANE = 1152;                  // bytes per plane buffer: 48 zeros, 1024 samples, 80 zeros
+    static constexpr int NPLANES = 12;                  // [copy][channel a,b,c][h,l]; copy 1 = copy 0 advanced by 8 bytes
+    static constexpr int FRAME = NPLANES * PLANE;       // 13 824 bytes of planes per frame
+    static constexpr int NJ = 96;                       // lag slots kept (j = 0..95), j in [PAD-L, PAD+L] are real
+    static constexpr int NL = 2 * L + 1;
+    static constexpr int ZP = 136;                      // words per (class, phase) column of the transposing scratch
+    static constexpr int TCOLS = 144;                   // TMEM columns per frame: 3 pairs x {hh, mid, ll} x 16
+    static constexpr int PREP_WARPS = 4, SETS = 3, BUFS = 2;
+    static_assert(PAD >= L && PAD + L + 15 < 128 && PAD + L < NJ, "lag window must fit the 128-row tile");
+    static_assert(127 + 16 * 63 + 8 < PLANE, "A operand reads stay inside a plane buffer");
+};
+
+template <int L>
+struct UmmaSmem {
+    using G = UmmaGeo<L>;
+    alignas(128) uint8_t planes[G::PREP_WARPS][G::BUFS][G::FRAME];
+    alignas(16) int z[G::SETS][3][8][G::ZP];            // [set][class][phase][row - phase + 7]
+    alignas(16) long long curve[G::SETS][3][G::NJ];     // raw curves by lag index (input of epilogue_warp)
+    alignas(16) long long part[G::SETS][3][4];          // per-warp arg-max keys
+    alignas(16) uint32_t win2[G::N];
+    float gauss[2 * L + 1];
+    alignas(8) uint64_t full[G::SETS], empty[G::SETS], sfree[G::PREP_WARPS][G::BUFS];
+    uint32_t tmem_base;
+    unsigned issue_seq;                                 // next frame (CTA-local sequence number) whose MMAs may be issued
+};
+
+// ---------------------------------------------------------------- tcgen05 wrappers
+// shared-memory matrix descriptor, no swizzle, version 1; lo word = start address and LBO (16-byte units)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)(((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16)) | ((uint64_t)((sbo_bytes >> 4) | 0x4000u) << 32);
+}
+// instruction descriptor: S32 accumulators, signed int8 A and B, both MN-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc(int n)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ int dp2a_lo_acc(uint32_t a, uint32_t b, int c)
+{
+    int r;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ int dp2a_hi_acc(uint32_t a, uint32_t b, int c)
+{
+    int r;
+    asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// 16 consecutive samples -> balanced digit planes.  As imma_prep16, but the product carries +0x8000 (the IDP addend,
+// free): q = a * 2W + 0x8000, so byte 2 of q is h = (w + 128) >> 8 and byte 1 of q is l with its top bit flipped.
+// ref: rolling_buffer.c:66, buffer.c:16, buffer.c:8-9.
+__device__ __forceinline__ void umma_prep16(const uint32_t (&rw)[4], int mean, const uint32_t *win2, int i0,
+                                            uint32_t (&hi)[4], uint32_t (&lo)[4])
+{
+    const uint32_t k4 = (uint32_t)((256 - mean) & 0xFF) * 0x01010101u;
+    const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
+#pragma unroll
+    for (int w4 = 0; w4 < 4; w4++) {
+        const uint4 ww = *reinterpret_cast<const uint4 *>(&win2[imma_win_index(i0 + 4 * w4)]);
+        const uint32_t d = sub_bytes(rw[w4], k7, kM);
+        const int p0 = dp2a_lo_acc(ww.x, d, 0x8000), p1 = dp2a_lo_acc(ww.y, d, 0x8000);
+        const int p2 = dp2a_hi_acc(ww.z, d, 0x8000), p3 = dp2a_hi_acc(ww.w, d, 0x8000);
+        const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
+        const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
+        lo[w4] = __byte_perm(t01, t23, 0x5410) ^ 0x80808080u;
+        hi[w4] = __byte_perm(t01, t23, 0x7632);
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(512, 1) at_fused_umma_kernel(const AtFusedParams p)
+{
+    using G = UmmaGeo<L>;
+    using S = UmmaSmem<L>;
+    constexpr int N = G::N, PAD = G::PAD, PLANE = G::PLANE;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    S &s = *reinterpret_cast<S *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- one-time CTA set-up: zero the planes (pads stay zero), window, Gaussian factors, barriers, TMEM
+    for (int i = tid; i < (int)(sizeof(s.planes) / 16); i += 512)
+        reinterpret_cast<uint4 *>(&s.planes[0][0][0])[i] = make_uint4(0, 0, 0, 0);
+    imma_win_fill(s.win2, p.window, N, tid, 512);
+    for (int i = tid; i < 2 * L + 1; i += 512) s.gauss[i] = p.gauss[i];
+    if (tid == 0) {
+        for (int k = 0; k < G::SETS; k++) { mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], 4); }
+        for (int w = 0; w < G::PREP_WARPS; w++)
+            for (int b = 0; b < G::BUFS; b++) mbar_init(&s.sfree[w][b], 1);
+        s.issue_seq = 0;
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s.tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const unsigned long long nf = p.n_frames, gstride = gridDim.x;
+
+    if (warp < G::PREP_WARPS) {
+        // =================================================================== prep warps + MMA issue
+        for (unsigned long long i = warp;; i += G::PREP_WARPS) {
+            const unsigned long long f = blockIdx.x + gstride * i;
+            if (f >= nf) break;
+            const unsigned jseq = (unsigned)(i / G::PREP_WARPS), b = jseq & 1, v = jseq >> 1;
+            uint8_t *const buf = &s.planes[warp][b][0];
+            auto plane = [&](int copy, int ch, int hl) -> uint8_t * { return buf + ((copy * 3 + ch) * 2 + hl) * PLANE; };
+            const uint8_t *src = p.adc + f * (unsigned long long)(3 * N);
+            const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
+
+            // channel sums -> floor mean (rolling_buffer.c:48-64); the sum is rotation invariant
+            uint4 raw[6];
+            int mean[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                unsigned sum = 0;
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const uint4 x = ldg_stream(src + ch * N + q * 512 + lane * 16);
+                    raw[ch * 2 + q] = x;
+                    sum = __dp4a(x.x, 0x01010101u, sum); sum = __dp4a(x.y, 0x01010101u, sum);
+                    sum = __dp4a(x.z, 0x01010101u, sum); sum = __dp4a(x.w, 0x01010101u, sum);
+                }
+                sum = __reduce_add_sync(0xffffffffu, sum);
+                mean[ch] = (int)(sum >> 10);
+            }
+            // the tensor core must be done with this buffer (frame i - 8 of this CTA)
+            if (v >= 1) mbar_wait(&s.sfree[warp][b], (v - 1) & 1);
+            if (!(p.debug_skip & 1))
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int j0 = q * 512 + lane * 16;
+                    const uint4 x = raw[ch * 2 + q];
+                    const uint32_t rw[4] = {x.x, x.y, x.z, x.w};
+                    if ((head & 15) == 0) {
+                        const int i0 = (j0 - head) & (N - 1);
+                        uint32_t hi[4], lo[4];
+                        umma_prep16(rw, mean[ch], s.win2, i0, hi, lo);
+                        *reinterpret_cast<uint4 *>(plane(0, ch, 0) + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(plane(0, ch, 1) + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        // second copy, advanced by 8 bytes: sample i sits at PAD - 8 + i
+                        *reinterpret_cast<uint2 *>(plane(1, ch, 0) + PAD - 8 + i0) = make_uint2(hi[0], hi[1]);
+                        *reinterpret_cast<uint2 *>(plane(1, ch, 0) + PAD + i0) = make_uint2(hi[2], hi[3]);
+                        *reinterpret_cast<uint2 *>(plane(1, ch, 1) + PAD - 8 + i0) = make_uint2(lo[0], lo[1]);
+                        *reinterpret_cast<uint2 *>(plane(1, ch, 1) + PAD + i0) = make_uint2(lo[2], lo[3]);
+                    } else {   // ring head not 16-aligned: scalar stores (rare; capture heads are arbitrary)
+#pragma unroll
+                        for (int e = 0; e < 16; e++) {
+                            const int ii = (j0 + e - head) & (N - 1);
+                            const int q24 = imma_prep1(rw[e >> 2] >> (8 * (e & 3)), mean[ch], s.win2, ii) + 0x8000;
+                            const uint8_t hb = (uint8_t)(q24 >> 16), lb = (uint8_t)((q24 >> 8) ^ 0x80);
+                            plane(0, ch, 0)[PAD + ii] = hb; plane(0, ch, 1)[PAD + ii] = lb;
+                            plane(1, ch, 0)[PAD - 8 + ii] = hb; plane(1, ch, 1)[PAD - 8 + ii] = lb;
+                        }
+                    }
+                }
+                if (p.power) {   // rolling_buffer.c:68-70
+                    long long acc = 0;
+                    for (int k = lane; k < N; k += 32) { const int dv = (int)src[ch * N + k] - mean[ch]; acc += (long long)dv * dv; }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) p.power[f * 3 + ch] = acc;
+                }
+            }
+            __syncwarp();
+            if (p.windowed)
+                for (int idx = lane; idx < 3 * N; idx += 32) {
+                    const int ch = idx / N, ii = idx % N;
+                    p.windowed[f * (unsigned long long)(3 * N) + idx] =
+                        (int16_t)((int)(signed char)plane(0, ch, 0)[PAD + ii] * 256 + (int)(signed char)plane(0, ch, 1)[PAD + ii]);
+                }
+            {   // next frame of this warp -> L1/L2
+                const unsigned long long fn = f + gstride * G::PREP_WARPS;
+                if (fn < nf && lane * 128 < 3 * N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.adc + fn * (unsigned long long)(3 * N) + lane * 128));
+            }
+            fence_proxy_async();          // this lane's plane bytes -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) {
+                // Frames are issued strictly in sequence: a parity wait on an mbarrier is only meaningful for the
+                // current or the immediately preceding phase, so the uses of a TMEM slot must not overtake each other.
+                volatile unsigned *seq = &s.issue_seq;
+                while (*seq != (unsigned)i) __nanosleep(32);
+                const unsigned slot = (unsigned)(i % G::SETS), u = (unsigned)(i / G::SETS);
+                if (u >= 1) mbar_wait(&s.empty[slot], (u - 1) & 1);     // the epilogue set has drained the slot
+                tc_fence_after();
+                const uint32_t base = smem_u32(buf);
+                constexpr uint32_t I32 = umma_idesc(32), I16 = umma_idesc(16);
+                // pairs (x, y): (a, b), (a, c), (b, c) -- order of the reference's new_corr_ab / ac / bc
+                if (!(p.debug_skip & 2))
+#pragma unroll
+                for (int pr = 0; pr < 3; pr++) {
+                    const int xc = pr == 2 ? 1 : 0, yc = pr == 0 ? 1 : 2;
+                    const uint32_t cb = tmem + slot * G::TCOLS + pr * 48;
+#pragma unroll
+                    for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+                        for (int copy = 0; copy < 2; copy++) {
+                            const uint32_t ya = base + ((copy * 3 + yc) * 2) * PLANE + 512 * kk;          // y.h plane, K step kk
+                            const uint32_t xa = base + ((copy * 3 + xc) * 2) * PLANE + PAD + 512 * kk;    // x.h plane (x.l follows)
+                            const uint64_t a_h = umma_desc(ya, 128, 16), a_l = umma_desc(ya + PLANE, 128, 16);
+                            const uint64_t b_hl = umma_desc(xa, 128, PLANE), b_l = umma_desc(xa + PLANE, 128, PLANE);
+                            if (kk == 0 && copy == 0) {
+                                umma_i8(cb + 0, a_h, b_hl, I32, 0);       // [h.h | h.l]     overwrite
+                                umma_i8(cb + 16, a_l, b_hl, I16, 1);      // mid += l.h
+                                umma_i8(cb + 32, a_l, b_l, I16, 0);       // l.l             overwrite
+                            } else {
+                                umma_i8(cb + 0, a_h, b_hl, I32, 1);       // [h.h | h.l]
+                                umma_i8(cb + 16, a_l, b_hl, I32, 1);      // [l.h | l.l]
+                            }
+                        }
+                }
+                umma_commit(&s.full[slot]);
+                umma_commit(&s.sfree[warp][b]);
+                __threadfence_block();
+                *seq = (unsigned)i + 1;
+            }
+            __syncwarp();
+        }
+    } else {
+        // =================================================================== epilogue sets
+        const int set = (warp - G::PREP_WARPS) >> 2, wq = warp & 3, tset = wq * 32 + lane;   // tset = TMEM lane = tile row m
+        int *const z = &s.z[set][0][0][0];
+        long long *const curve = &s.curve[set][0][0];
+        for (unsigned long long i = set;; i += G::SETS) {
+            const unsigned long long f = blockIdx.x + gstride * i;
+            if (f >= nf) break;
+            const unsigned u = (unsigned)(i / G::SETS);
+            mbar_wait(&s.full[set], u & 1);
+            tc_fence_after();
+            if (p.debug_skip & 4) {       // timing experiments: drain the slot without looking at it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.empty[set]);
+                continue;
+            }
+#pragma unroll 1
+            for (int pr = 0; pr < 3; pr++) {
+                uint32_t t[3][8];
+                const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + set * G::TCOLS + pr * 48;
+                tmem_ld8(ta, t[0]); tmem_ld8(ta + 16, t[1]); tmem_ld8(ta + 32, t[2]);
+                tmem_ld_wait();
+                if (pr == 2) {            // accumulators are in registers: hand the slot back to the tensor core
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s.empty[set]);
+                }
+                // transposing scatter: entry (m, phi) belongs to lag index j = m - phi
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int ph = 0; ph < 8; ph++) z[(c * 8 + ph) * G::ZP + tset - ph + 7] = (int)t[c][ph];
+                named_bar(1 + set, 128);
+                long long key = LLONG_MIN;
+                if (tset < G::NJ) {
+                    const int j = tset;
+                    int hh = 0, mid = 0, ll = 0;
+#pragma unroll
+                    for (int ph = 0; ph < 8; ph++) {
+                        hh += z[(0 * 8 + ph) * G::ZP + j + 7];
+                        mid += z[(1 * 8 + ph) * G::ZP + j + 7];
+                        ll += z[(2 * 8 + ph) * G::ZP + j + 7];
+                    }
+                    const long long val = 65536LL * hh + 256LL * mid + (long long)ll;
+                    curve[pr * G::NJ + j] = val;
+                    if (j >= PAD - L && j <= PAD + L) key = val * 128 + (127 - j);   // largest value, then lowest lag
+                }
+                key = warp_max_i64(key);
+                if (lane == 0) s.part[set][pr][wq] = key;
+                named_bar(1 + set, 128);
+            }
+            if (wq == 0) {
+                int best3[3];
+                long long peak[3];
+#pragma unroll
+                for (int pr = 0; pr < 3; pr++) {
+                    long long key = s.part[set][pr][0];
+                    if (s.part[set][pr][1] > key) key = s.part[set][pr][1];
+                    if (s.part[set][pr][2] > key) key = s.part[set][pr][2];
+                    best3[pr] = 127 - (int)(key & 127) - PAD;
+                    peak[pr] = key >> 7;
+                }
+                if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? best3[0] : (lane == 1 ? best3[1] : best3[2]);
+                const bool extras = p.gate || p.raw || p.corr || p.cell || p.highest || p.xy || p.classes;
+                bool settled = !extras;
+                if (extras && !(p.raw || p.corr || p.classes))
+                    settled = peak_tuple_lookup<L>(p, f, lane, best3[0], best3[1], best3[2], peak);
+                if (!settled) epilogue_warp<L, PAD, G::NJ, G::NJ>(curve, best3[0], best3[1], best3[2], s.gauss, p, f, lane);
+            }
+            named_bar(1 + set, 128);      // curve / part / z are rewritten by the next frame of this set
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+}
+
+} // namespace atk
+
+bool at_fused_umma_supports(const AtShape &sh)
+{
+    return sh.n_mics == 3 && sh.n_bits == 10 && (sh.max_shift == 46 || sh.max_shift == 44);
+}
+
+template <int L>
+static cudaError_t launch_umma(const AtFusedParams &p, int sm_count, cudaStream_t st)
+{
+    auto kern = atk::at_fused_umma_kernel<L>;
+    const int smem = (int)sizeof(atk::UmmaSmem<L>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    unsigned long long grid = (unsigned long long)sm_count;
+    if (grid > p.n_frames) grid = p.n_frames;
+    if (grid == 0) return cudaSuccess;
+    kern<<<(unsigned)grid, 512, smem, st>>>(p);
+    at_count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t at_launch_fused_umma(const AtShape &sh, const AtFusedParams &p, int sm_count, cudaStream_t st)
+{
+    if (p.sig16 || !at_fused_umma_supports(sh)) return cudaErrorInvalidValue;
+    return sh.max_shift == 46 ? launch_umma<46>(p, sm_count, st) : launch_umma<44>(p, sm_count, st);
+}

@@ -13,7 +13,7 @@ from oracle_bindings import CELLS, CORR_DT, HALF_H, HALF_W, HEIGHT, PX_PER_M, RA
 pytestmark = pytest.mark.gpu
 
 ALL = ("lags", "corr", "raw", "cell", "highest", "xy", "gate", "classes", "windowed", "power")
-KERNELS = ("imad", "imma", "imma_lm")
+KERNELS = ("imad", "imma", "imma_lm", "umma")
 
 
 def _torch():
