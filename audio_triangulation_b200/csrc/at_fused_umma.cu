@@ -14,20 +14,29 @@
 //
 // int16 samples are split into balanced signed digits w = 256 h + l, h and l both in [-128, 127] (possible because
 // the windowed samples stay inside [-32767, 32511]); corr = 65536 (h.h) + 256 (h.l + l.h) + (l.l) as in the
-// mma.sync kernel, each class in its own 16 TMEM columns, int32 (|sum| < 2^26), recombined in int64: bit-exact.
+// mma.sync kernel, each of the four digit products in its own 16 TMEM columns, int32 (|sum| < 2^26), recombined in
+// int64: bit-exact.  An MMA of this shape costs about (A bytes + B bytes) / 128 cycles whatever N is (measured,
+// tools/probes/umma_probe.cu: 46 cycles at N = 16..64), so the x planes are batched into one wide B operand.
 //
 // The diagonal sums are the CUDA cores' job.  To halve them every plane is stored twice, the second copy advanced by
 // 8 bytes, and both copies are accumulated into the same tile:  D2[m][phi] = D[m][phi] + D[m+8][phi+8]  for
 // phi = 0..7, i.e. two entries of the same diagonal; corr[s] = sum_{phi<8} D2[s + PAD + phi][phi].
 //
-// CTA = 16 warps, one CTA per SM, persistent:
-//   warps 0-3   prep: one frame each -- coalesced 16-byte loads, DC removal, <<8, window (as imma_prep16), digit
-//               planes to shared memory (both copies), then ONE lane issues the frame's 27 MMAs and commits them to
-//               two mbarriers (accumulators ready / planes free);
-//   warps 4-15  three epilogue sets of four warps, set k bound to TMEM slot k (144 columns): TMEM -> registers
-//               (warp w reads lane quadrant w % 4), transposing scatter through shared memory, diagonal sums,
-//               int64 recombination, first-max arg-max (correlations.c:20-23), then peak-tuple look-up or the
+// CTA = 16 warps, one CTA per SM, persistent, warp-specialised:
+//   warp 0      one lane issues, frame after frame, the 16 MMAs of a frame (2 K-steps x 2 copies x 4 y planes; the
+//               B operand is the four x planes a.h a.l b.h b.l side by side, N = 64) and commits them to two mbarriers
+//               (accumulators ready / planes free);
+//   warps 1-7   prep: one frame each -- coalesced 16-byte loads, DC removal, <<8, window (as imma_prep16), digit
+//               planes to shared memory (both copies), mbarrier arrive;
+//   warps 8-15  two epilogue sets of four warps, set k bound to TMEM slot k (192 columns = 12 tiles): TMEM ->
+//               registers (warp w reads lane quadrant w % 4), transposing scatter through shared memory, diagonal
+//               sums, int64 recombination, first-max arg-max (correlations.c:20-23), then peak-tuple look-up or the
 //               warp-scope epilogue of at_imma_common.cuh for everything else.
+//
+// Status (measured on the B200): bit-exact on every parity test, 152 M frames/s -- 0.71x the mma.sync
+// kernel, which therefore stays the default.  Two things bound it: an MMA of this shape costs ~63-73 cycles whatever
+// N <= 64 is (4 KB of A operand per instruction, fetched at ~64-128 B/clk: 16 MMAs = ~1 170 cycles per frame), and the
+// 9 x 8 x 128 diagonal terms per frame have to be added by the CUDA cores.
 #include <limits.h>
 #include <stdlib.h>
 
@@ -44,9 +53,9 @@ struct UmmaGeo {
     static constexpr int FRAME = NPLANES * PLANE;       // 13 824 bytes of planes per frame
     static constexpr int NJ = 96;                       // lag slots kept (j = 0..95), j in [PAD-L, PAD+L] are real
     static constexpr int NL = 2 * L + 1;
-    static constexpr int ZP = 136;                      // words per (class, phase) column of the transposing scratch
-    static constexpr int TCOLS = 144;                   // TMEM columns per frame: 3 pairs x {hh, mid, ll} x 16
-    static constexpr int PREP_WARPS = 4, SETS = 3, BUFS = 2;
+    static constexpr int ZP = 136;                      // words per (pair, class, phase) column of the transposing scratch
+    static constexpr int TCOLS = 192;                   // TMEM columns per frame: 12 tiles (3 pairs x {hh, hl, lh, ll}) x 16
+    static constexpr int PREP_WARPS = 7, SETS = 2;      // warp 0 issues the MMAs, warps 1-7 prepare, warps 8-15 = 2 epilogue sets
     static_assert(PAD >= L && PAD + L + 15 < 128 && PAD + L < NJ, "lag window must fit the 128-row tile");
     static_assert(127 + 16 * 63 + 8 < PLANE, "A operand reads stay inside a plane buffer");
 };
@@ -54,15 +63,14 @@ struct UmmaGeo {
 template <int L>
 struct UmmaSmem {
     using G = UmmaGeo<L>;
-    alignas(128) uint8_t planes[G::PREP_WARPS][G::BUFS][G::FRAME];
-    alignas(16) int z[G::SETS][3][8][G::ZP];            // [set][class][phase][row - phase + 7]
+    alignas(128) uint8_t planes[G::PREP_WARPS][G::FRAME];
+    alignas(16) int z[G::SETS][3][3][8][G::ZP];         // [set][pair][class][phase][row - phase + 7]
     alignas(16) long long curve[G::SETS][3][G::NJ];     // raw curves by lag index (input of epilogue_warp)
-    alignas(16) long long part[G::SETS][3][4];          // per-warp arg-max keys
+    alignas(16) long long part[G::SETS][3][4];          // per-block arg-max keys
     alignas(16) uint32_t win2[G::N];
     float gauss[2 * L + 1];
-    alignas(8) uint64_t full[G::SETS], empty[G::SETS], sfree[G::PREP_WARPS][G::BUFS];
+    alignas(8) uint64_t full[G::SETS], empty[G::SETS], ready[G::PREP_WARPS], sfree[G::PREP_WARPS];
     uint32_t tmem_base;
-    unsigned issue_seq;                                 // next frame (CTA-local sequence number) whose MMAs may be issued
 };
 
 // ---------------------------------------------------------------- tcgen05 wrappers
@@ -81,6 +89,21 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
                  :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// same with the descriptors given as (lo, hi) words: lo = start address and LBO, the only part that changes per MMA
+__device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+                 "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, {%7, %7, %7, %7}, p;\n\t}\n"
+                 :: "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
@@ -142,21 +165,19 @@ __global__ void __launch_bounds__(512, 1) at_fused_umma_kernel(const AtFusedPara
 {
     using G = UmmaGeo<L>;
     using S = UmmaSmem<L>;
-    constexpr int N = G::N, PAD = G::PAD, PLANE = G::PLANE;
+    constexpr int N = G::N, PAD = G::PAD, PLANE = G::PLANE, P = G::PREP_WARPS;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     S &s = *reinterpret_cast<S *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- one-time CTA set-up: zero the planes (pads stay zero), window, Gaussian factors, barriers, TMEM
     for (int i = tid; i < (int)(sizeof(s.planes) / 16); i += 512)
-        reinterpret_cast<uint4 *>(&s.planes[0][0][0])[i] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4 *>(&s.planes[0][0])[i] = make_uint4(0, 0, 0, 0);
     imma_win_fill(s.win2, p.window, N, tid, 512);
     for (int i = tid; i < 2 * L + 1; i += 512) s.gauss[i] = p.gauss[i];
     if (tid == 0) {
         for (int k = 0; k < G::SETS; k++) { mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], 4); }
-        for (int w = 0; w < G::PREP_WARPS; w++)
-            for (int b = 0; b < G::BUFS; b++) mbar_init(&s.sfree[w][b], 1);
-        s.issue_seq = 0;
+        for (int w = 0; w < P; w++) { mbar_init(&s.ready[w], 1); mbar_init(&s.sfree[w], 1); }
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -168,15 +189,53 @@ __global__ void __launch_bounds__(512, 1) at_fused_umma_kernel(const AtFusedPara
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
     const unsigned long long nf = p.n_frames, gstride = gridDim.x;
+    // frames of this CTA: f = blockIdx.x + gridDim.x * i, i = 0, 1, 2, ...; frame i is prepared by prep warp i % P,
+    // accumulated in TMEM slot i % SETS and finished by epilogue set i % SETS.  Every mbarrier is waited on in phase
+    // order by exactly one party (a parity wait only distinguishes the current from the preceding phase).
 
-    if (warp < G::PREP_WARPS) {
-        // =================================================================== prep warps + MMA issue
-        for (unsigned long long i = warp;; i += G::PREP_WARPS) {
+    if (warp == 0) {
+        // =================================================================== MMA issue (one elected lane, frames in order)
+        constexpr uint32_t I64 = umma_idesc(64), I32 = umma_idesc(32);
+        constexpr uint32_t LBO = (128u >> 4) << 16;                     // K groups of 8 rows are 128 bytes apart
+        constexpr uint32_t HI_A = (16u >> 4) | 0x4000u;                 // A: MN chunks 16 bytes apart (Hankel), version 1
+        constexpr uint32_t HI_B = ((uint32_t)PLANE >> 4) | 0x4000u;     // B: one 16-phase chunk per x plane
+        for (unsigned long long i = 0;; i++) {
+            if (blockIdx.x + gstride * i >= nf) break;
+            const unsigned w = (unsigned)(i % P), v = (unsigned)(i / P), slot = (unsigned)(i % G::SETS), u = (unsigned)(i / G::SETS);
+            mbar_wait(&s.ready[w], v & 1);                          // planes of frame i are in shared memory
+            if (u >= 1) mbar_wait(&s.empty[slot], (u - 1) & 1);     // the epilogue set has drained the slot
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t b16 = (smem_u32(&s.planes[w][0]) >> 4) + LBO;   // start-address field of plane a.h, copy 0
+                const uint32_t cb = tmem + slot * G::TCOLS;
+                if (!(p.debug_skip & 2))
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+                    for (int copy = 0; copy < 2; copy++) {
+                        const uint32_t acc = (kk | copy) ? 1u : 0u;
+                        const uint32_t pl = b16 + (uint32_t)((copy * 6 * PLANE + 512 * kk) >> 4);   // plane a.h of this copy, K step kk
+                        const uint32_t xb = pl + (PAD >> 4);            // B: x planes a.h a.l b.h b.l side by side
+                        // A: one y plane, 128 Hankel rows.  Tiles: [x.h | x.l] per x channel.
+                        umma_i8_lohi(cb + 0, pl + 4 * (PLANE >> 4), HI_A, xb, HI_B, I64, acc);     // c.h: ac hh, ac hl, bc hh, bc hl
+                        umma_i8_lohi(cb + 64, pl + 5 * (PLANE >> 4), HI_A, xb, HI_B, I64, acc);    // c.l: ac lh, ac ll, bc lh, bc ll
+                        umma_i8_lohi(cb + 128, pl + 2 * (PLANE >> 4), HI_A, xb, HI_B, I32, acc);   // b.h: ab hh, ab hl
+                        umma_i8_lohi(cb + 160, pl + 3 * (PLANE >> 4), HI_A, xb, HI_B, I32, acc);   // b.l: ab lh, ab ll
+                    }
+                umma_commit(&s.full[slot]);
+                umma_commit(&s.sfree[w]);
+            }
+            __syncwarp();
+        }
+    } else if (warp <= P) {
+        // =================================================================== prep warps
+        const int w = warp - 1;
+        uint8_t *const buf = &s.planes[w][0];
+        auto plane = [&](int copy, int ch, int hl) -> uint8_t * { return buf + ((copy * 3 + ch) * 2 + hl) * PLANE; };
+        for (unsigned long long i = w;; i += P) {
             const unsigned long long f = blockIdx.x + gstride * i;
             if (f >= nf) break;
-            const unsigned jseq = (unsigned)(i / G::PREP_WARPS), b = jseq & 1, v = jseq >> 1;
-            uint8_t *const buf = &s.planes[warp][b][0];
-            auto plane = [&](int copy, int ch, int hl) -> uint8_t * { return buf + ((copy * 3 + ch) * 2 + hl) * PLANE; };
+            const unsigned v = (unsigned)(i / P);
             const uint8_t *src = p.adc + f * (unsigned long long)(3 * N);
             const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
 
@@ -196,8 +255,12 @@ __global__ void __launch_bounds__(512, 1) at_fused_umma_kernel(const AtFusedPara
                 sum = __reduce_add_sync(0xffffffffu, sum);
                 mean[ch] = (int)(sum >> 10);
             }
-            // the tensor core must be done with this buffer (frame i - 8 of this CTA)
-            if (v >= 1) mbar_wait(&s.sfree[warp][b], (v - 1) & 1);
+            {   // next frame of this warp -> L1/L2
+                const unsigned long long fn = f + gstride * P;
+                if (fn < nf && lane * 128 < 3 * N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.adc + fn * (unsigned long long)(3 * N) + lane * 128));
+            }
+            // the tensor core must be done with this warp's previous frame
+            if (v >= 1) mbar_wait(&s.sfree[w], (v - 1) & 1);
             if (!(p.debug_skip & 1))
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
@@ -243,58 +306,17 @@ __global__ void __launch_bounds__(512, 1) at_fused_umma_kernel(const AtFusedPara
                     p.windowed[f * (unsigned long long)(3 * N) + idx] =
                         (int16_t)((int)(signed char)plane(0, ch, 0)[PAD + ii] * 256 + (int)(signed char)plane(0, ch, 1)[PAD + ii]);
                 }
-            {   // next frame of this warp -> L1/L2
-                const unsigned long long fn = f + gstride * G::PREP_WARPS;
-                if (fn < nf && lane * 128 < 3 * N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.adc + fn * (unsigned long long)(3 * N) + lane * 128));
-            }
             fence_proxy_async();          // this lane's plane bytes -> visible to the tensor core's reads
             __syncwarp();
-            if (lane == 0) {
-                // Frames are issued strictly in sequence: a parity wait on an mbarrier is only meaningful for the
-                // current or the immediately preceding phase, so the uses of a TMEM slot must not overtake each other.
-                volatile unsigned *seq = &s.issue_seq;
-                while (*seq != (unsigned)i) __nanosleep(32);
-                const unsigned slot = (unsigned)(i % G::SETS), u = (unsigned)(i / G::SETS);
-                if (u >= 1) mbar_wait(&s.empty[slot], (u - 1) & 1);     // the epilogue set has drained the slot
-                tc_fence_after();
-                const uint32_t base = smem_u32(buf);
-                constexpr uint32_t I32 = umma_idesc(32), I16 = umma_idesc(16);
-                // pairs (x, y): (a, b), (a, c), (b, c) -- order of the reference's new_corr_ab / ac / bc
-                if (!(p.debug_skip & 2))
-#pragma unroll
-                for (int pr = 0; pr < 3; pr++) {
-                    const int xc = pr == 2 ? 1 : 0, yc = pr == 0 ? 1 : 2;
-                    const uint32_t cb = tmem + slot * G::TCOLS + pr * 48;
-#pragma unroll
-                    for (int kk = 0; kk < 2; kk++)
-#pragma unroll
-                        for (int copy = 0; copy < 2; copy++) {
-                            const uint32_t ya = base + ((copy * 3 + yc) * 2) * PLANE + 512 * kk;          // y.h plane, K step kk
-                            const uint32_t xa = base + ((copy * 3 + xc) * 2) * PLANE + PAD + 512 * kk;    // x.h plane (x.l follows)
-                            const uint64_t a_h = umma_desc(ya, 128, 16), a_l = umma_desc(ya + PLANE, 128, 16);
-                            const uint64_t b_hl = umma_desc(xa, 128, PLANE), b_l = umma_desc(xa + PLANE, 128, PLANE);
-                            if (kk == 0 && copy == 0) {
-                                umma_i8(cb + 0, a_h, b_hl, I32, 0);       // [h.h | h.l]     overwrite
-                                umma_i8(cb + 16, a_l, b_hl, I16, 1);      // mid += l.h
-                                umma_i8(cb + 32, a_l, b_l, I16, 0);       // l.l             overwrite
-                            } else {
-                                umma_i8(cb + 0, a_h, b_hl, I32, 1);       // [h.h | h.l]
-                                umma_i8(cb + 16, a_l, b_hl, I32, 1);      // [l.h | l.l]
-                            }
-                        }
-                }
-                umma_commit(&s.full[slot]);
-                umma_commit(&s.sfree[warp][b]);
-                __threadfence_block();
-                *seq = (unsigned)i + 1;
-            }
-            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.ready[w]);
         }
     } else {
         // =================================================================== epilogue sets
-        const int set = (warp - G::PREP_WARPS) >> 2, wq = warp & 3, tset = wq * 32 + lane;   // tset = TMEM lane = tile row m
-        int *const z = &s.z[set][0][0][0];
+        const int set = (warp - 1 - P) >> 2, wq = warp & 3, tset = wq * 32 + lane;   // tset = TMEM lane = tile row m
+        int *const z = &s.z[set][0][0][0][0];
         long long *const curve = &s.curve[set][0][0];
+        // TMEM column of the hh tile of each pair (x, y) = (a,b), (a,c), (b,c); hl follows at +16
+        // and (lh, ll) sit OFF_L columns further (the tiles of the y.l plane)
         for (unsigned long long i = set;; i += G::SETS) {
             const unsigned long long f = blockIdx.x + gstride * i;
             if (f >= nf) break;
@@ -307,41 +329,46 @@ __global__ void __launch_bounds__(512, 1) at_fused_umma_kernel(const AtFusedPara
                 if (lane == 0) mbar_arrive(&s.empty[set]);
                 continue;
             }
-#pragma unroll 1
+            const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + set * G::TCOLS;
+#pragma unroll
             for (int pr = 0; pr < 3; pr++) {
-                uint32_t t[3][8];
-                const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + set * G::TCOLS + pr * 48;
-                tmem_ld8(ta, t[0]); tmem_ld8(ta + 16, t[1]); tmem_ld8(ta + 32, t[2]);
+                const uint32_t c_hh = pr == 0 ? 128 : (pr == 1 ? 0 : 32), off_l = pr == 0 ? 32 : 64;
+                uint32_t hh[8], hl[8], lh[8], ll[8];
+                tmem_ld8(ta + c_hh, hh); tmem_ld8(ta + c_hh + 16, hl);
+                tmem_ld8(ta + c_hh + off_l, lh); tmem_ld8(ta + c_hh + off_l + 16, ll);
                 tmem_ld_wait();
-                if (pr == 2) {            // accumulators are in registers: hand the slot back to the tensor core
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s.empty[set]);
-                }
                 // transposing scatter: entry (m, phi) belongs to lag index j = m - phi
+                int *const zp = z + pr * 3 * 8 * G::ZP + tset + 7;
 #pragma unroll
-                for (int c = 0; c < 3; c++)
-#pragma unroll
-                    for (int ph = 0; ph < 8; ph++) z[(c * 8 + ph) * G::ZP + tset - ph + 7] = (int)t[c][ph];
-                named_bar(1 + set, 128);
-                long long key = LLONG_MIN;
-                if (tset < G::NJ) {
-                    const int j = tset;
-                    int hh = 0, mid = 0, ll = 0;
-#pragma unroll
-                    for (int ph = 0; ph < 8; ph++) {
-                        hh += z[(0 * 8 + ph) * G::ZP + j + 7];
-                        mid += z[(1 * 8 + ph) * G::ZP + j + 7];
-                        ll += z[(2 * 8 + ph) * G::ZP + j + 7];
-                    }
-                    const long long val = 65536LL * hh + 256LL * mid + (long long)ll;
-                    curve[pr * G::NJ + j] = val;
-                    if (j >= PAD - L && j <= PAD + L) key = val * 128 + (127 - j);   // largest value, then lowest lag
+                for (int ph = 0; ph < 8; ph++) {
+                    zp[(0 * 8 + ph) * G::ZP - ph] = (int)hh[ph];
+                    zp[(1 * 8 + ph) * G::ZP - ph] = (int)hl[ph] + (int)lh[ph];
+                    zp[(2 * 8 + ph) * G::ZP - ph] = (int)ll[ph];
                 }
-                key = warp_max_i64(key);
-                if (lane == 0) s.part[set][pr][wq] = key;
-                named_bar(1 + set, 128);
             }
+            tc_fence_before();            // accumulators are out of TMEM: hand the slot back to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.empty[set]);
+            named_bar(1 + set, 128);
+            // diagonal sums: 9 blocks of 32 lags (3 pairs x 3), block b -> warp b % 4
+            for (int b = wq; b < 9; b += 4) {
+                const int pr = b / 3, j = (b % 3) * 32 + lane;
+                const int *zr = z + pr * 3 * 8 * G::ZP + j + 7;
+                int hh = 0, mid = 0, ll = 0;
+#pragma unroll
+                for (int ph = 0; ph < 8; ph++) {
+                    hh += zr[(0 * 8 + ph) * G::ZP];
+                    mid += zr[(1 * 8 + ph) * G::ZP];
+                    ll += zr[(2 * 8 + ph) * G::ZP];
+                }
+                const long long val = 65536LL * hh + 256LL * mid + (long long)ll;
+                curve[pr * G::NJ + j] = val;
+                long long key = LLONG_MIN;
+                if (j >= PAD - L && j <= PAD + L) key = val * 128 + (127 - j);   // largest value, then lowest lag
+                key = warp_max_i64(key);
+                if (lane == 0) s.part[set][pr][b % 3] = key;
+            }
+            named_bar(1 + set, 128);
             if (wq == 0) {
                 int best3[3];
                 long long peak[3];

@@ -168,6 +168,11 @@ __global__ void __launch_bounds__(128) tput(const int8_t *gy, int reps, uint32_t
     long long t0 = clock64();
     if (tid == 0) {
         const uint64_t ad = make_desc(a0, lbo_a, sbo_a), bd = make_desc(b0, 128, 1152);
+        if (lbo_a & 1) {     // odd LBO flag: walk through different A and B addresses (no operand re-use between MMAs)
+            const uint32_t lbo = lbo_a & ~1u;
+            for (int r = 0; r < reps; r++)
+                umma_i8(tmem, make_desc(a0 + (uint32_t)(r & 7) * 1024, lbo, sbo_a), make_desc(b0 + (uint32_t)(r & 3) * 4608, 128, 1152), idesc, 1);
+        } else
         for (int r = 0; r < reps; r++) umma_i8(tmem, ad, bd, idesc, 1);
         umma_commit(smem_u32(&bar));
     }
@@ -242,6 +247,9 @@ int main()
     run_tput<16>(dy, dc, "A disjoint chunks (SBO 512, LBO 128)", 512, 128);
     run_tput<64>(dy, dc, "A disjoint chunks (SBO 512, LBO 128)", 512, 128);
     run_tput<256>(dy, dc, "A disjoint chunks (SBO 512, LBO 128)", 512, 128);
+    run_tput<64>(dy, dc, "Hankel A, new A and B every MMA", 16, 129);
+    run_tput<32>(dy, dc, "Hankel A, new A and B every MMA", 16, 129);
+    run_tput<128>(dy, dc, "Hankel A, new A and B every MMA", 16, 129);
     run_tput<16>(dy, dc, "A canonical (SBO 128, LBO 1024)", 128, 1024);
     run_tput<64>(dy, dc, "A canonical (SBO 128, LBO 1024)", 128, 1024);
     return 0;
