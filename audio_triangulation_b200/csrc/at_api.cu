@@ -328,8 +328,10 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
         kernel = (at_fused_imma_supports(sh) || at_fused_imma_cta_supports(sh)) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;   // IMMA_LM measured slower
     cudaError_t e;
     if (kernel == AT_KERNEL_UMMA) {
-        if (!at_fused_umma_supports(sh) || p.sig16) return fail(AT_EINVAL, "UMMA kernel has no instantiation for this shape");
-        e = at_launch_fused_umma(sh, p, c->sm_count, st);
+        if (p.sig16) return fail(AT_EINVAL, "UMMA kernels take ADC bytes, not prepared int16 frames");
+        if (at_fused_umma_supports(sh)) e = at_launch_fused_umma(sh, p, c->sm_count, st);             // 3 mics x 1024
+        else if (at_fused_umma_m_supports(sh)) e = at_launch_fused_umma_m(sh, p, c->sm_count, st);    // 8 mics x 1024 / 4096
+        else return fail(AT_EINVAL, "UMMA kernel has no instantiation for this shape");
     } else if (kernel == AT_KERNEL_IMMA_LM) {
         if (!at_fused_imma3_supports(sh)) return fail(AT_EINVAL, "IMMA-LM kernel has no instantiation for this shape");
         e = at_launch_fused_imma3(sh, p, c->sm_count, st);

@@ -178,15 +178,18 @@ struct EpiSmem {
     int red_i[32];
 };
 
-// curve[][] holds the raw correlation sums.  All THREADS threads call; contains __syncthreads().
-template <int NMICS, int NBITS, int L, int THREADS>
+// curve[][] holds the raw correlation sums.  All THREADS threads of the group call; it synchronises the group with
+// barrier BAR (BAR = 0 and THREADS = blockDim.x: the whole CTA, i.e. __syncthreads; a warp-specialised kernel passes its
+// own barrier id and the index of the thread within the group).
+template <int NMICS, int NBITS, int L, int THREADS, int BAR = 0>
 __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const float *gauss_s,
-                                         const AtFusedParams &p, unsigned long long f)
+                                         const AtFusedParams &p, unsigned long long f, int tid = threadIdx.x)
 {
     using G = Geo<NBITS, L>;
     constexpr int P = NMICS * (NMICS - 1) / 2, NL = G::NL, OFF = G::PADL - L; // curve index of lag -L
     constexpr int NWARPS = THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
+    auto group_sync = [] { asm volatile("bar.sync %0, %1;" :: "n"(BAR), "n"(THREADS) : "memory"); };
 
     // (1) arg-max per pair (correlations.c:20-23): one warp per pair
     for (int pr = warp; pr < P; pr += NWARPS) {
@@ -201,7 +204,7 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
             if (p.lags) p.lags[f * P + pr] = b.i - L;
         }
     }
-    __syncthreads();
+    group_sync();
     if (p.gate && tid == 0) {           // sample_compute.h:124-134
         int tot = 0;
         for (int pr = 0; pr < P; pr++) tot += e.best[pr] * e.best[pr];
@@ -213,7 +216,7 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
     }
     const bool need_gauss = p.corr || p.cell || p.highest || p.xy || p.classes;
     if (!need_gauss) return;
-    __syncthreads();   // raw reads done before the in-place re-weighting
+    group_sync();   // raw reads done before the in-place re-weighting
 
     // (2) Gaussian re-weighting in place (correlations.c:26-33)
     for (int idx = tid; idx < P * NL; idx += THREADS) {
@@ -223,7 +226,7 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
         const float c = __ll2float_rn(e.curve[pr][OFF + li]);
         e.curve[pr][OFF + li] = __float2ll_rz(__fmul_rn(c, gauss_s[d]));
     }
-    __syncthreads();
+    group_sync();
     if (p.corr) {
         if (p.corr_struct) {   // struct correlations_t [F][P]: 93 x int64, int best_shift, pad, uint64 last_update
             long long *base = reinterpret_cast<long long *>(p.corr) + f * (unsigned long long)(P * (NL + 2));
@@ -253,7 +256,7 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
     }
     b = warp_best(b);
     if (lane == 0) { e.red_v[warp] = b.v; e.red_i[warp] = b.i; }
-    __syncthreads();
+    group_sync();
     if (warp == 0) {
         Best r = {LLONG_MIN, 0x7fffffff};
         if (lane < NWARPS) { r.v = e.red_v[lane]; r.i = e.red_i[lane]; }
@@ -272,7 +275,7 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
         }
     }
     if (p.classes) {   // vga_heatmap.h:111-126, colour codes of lib/vga/vga16_graphics.h:31-34
-        __syncthreads();
+        group_sync();
         const long long top = e.red_v[0];
         const long long tw = (top * 63) >> 6, tg = (top * 31) >> 5, tr = (top * 15) >> 4, tb = (top * 7) >> 3;
         for (int c = tid; c < p.n_cells; c += THREADS) {

@@ -41,6 +41,7 @@
 #include <stdlib.h>
 
 #include "at_imma_common.cuh"
+#include "at_umma_common.cuh"
 
 namespace atk {
 
@@ -72,93 +73,6 @@ struct UmmaSmem {
     alignas(8) uint64_t full[G::SETS], empty[G::SETS], ready[G::PREP_WARPS], sfree[G::PREP_WARPS];
     uint32_t tmem_base;
 };
-
-// ---------------------------------------------------------------- tcgen05 wrappers
-// shared-memory matrix descriptor, no swizzle, version 1; lo word = start address and LBO (16-byte units)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
-{
-    return (uint64_t)(((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16)) | ((uint64_t)((sbo_bytes >> 4) | 0x4000u) << 32);
-}
-// instruction descriptor: S32 accumulators, signed int8 A and B, both MN-major, M = 128
-__host__ __device__ constexpr uint32_t umma_idesc(int n)
-{
-    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
-                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-// same with the descriptors given as (lo, hi) words: lo = start address and LBO, the only part that changes per MMA
-__device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                             uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-                 "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, {%7, %7, %7, %7}, p;\n\t}\n"
-                 :: "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void named_bar(int id, int nthreads)
-{
-    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ int dp2a_lo_acc(uint32_t a, uint32_t b, int c)
-{
-    int r;
-    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
-__device__ __forceinline__ int dp2a_hi_acc(uint32_t a, uint32_t b, int c)
-{
-    int r;
-    asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-    return r;
-}
-
-// 16 consecutive samples -> balanced digit planes.  As imma_prep16, but the product carries +0x8000 (the IDP addend,
-// free): q = a * 2W + 0x8000, so byte 2 of q is h = (w + 128) >> 8 and byte 1 of q is l with its top bit flipped.
-// ref: rolling_buffer.c:66, buffer.c:16, buffer.c:8-9.
-__device__ __forceinline__ void umma_prep16(const uint32_t (&rw)[4], int mean, const uint32_t *win2, int i0,
-                                            uint32_t (&hi)[4], uint32_t (&lo)[4])
-{
-    const uint32_t k4 = (uint32_t)((256 - mean) & 0xFF) * 0x01010101u;
-    const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
-#pragma unroll
-    for (int w4 = 0; w4 < 4; w4++) {
-        const uint4 ww = *reinterpret_cast<const uint4 *>(&win2[imma_win_index(i0 + 4 * w4)]);
-        const uint32_t d = sub_bytes(rw[w4], k7, kM);
-        const int p0 = dp2a_lo_acc(ww.x, d, 0x8000), p1 = dp2a_lo_acc(ww.y, d, 0x8000);
-        const int p2 = dp2a_hi_acc(ww.z, d, 0x8000), p3 = dp2a_hi_acc(ww.w, d, 0x8000);
-        const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
-        const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
-        lo[w4] = __byte_perm(t01, t23, 0x5410) ^ 0x80808080u;
-        hi[w4] = __byte_perm(t01, t23, 0x7632);
-    }
-}
 
 template <int L>
 __global__ void __launch_bounds__(512, 1) at_fused_umma_kernel(const AtFusedParams p)

@@ -1,0 +1,290 @@
+// at_fused_umma_m.cu -- tcgen05 (UMMA) localization kernel for 8-microphone arrays (28 pairs), 1024- or 4096-sample
+// frames (BASELINE config 4).  Same polyphase Hankel formulation and digit arithmetic as at_fused_umma.cu:
+//     D[m][phi] = sum_q Y[m + 16 q] * x[phi + 16 q],   corr[s] = sum_phi D[s + PAD + phi][phi],
+// A = one digit plane of the y microphone read as an overlapping MN-major Hankel operand, B = the digit planes of ALL x
+// microphones below y side by side.  With 8 microphones B is up to 14 planes wide (N = 224): here the tensor core works
+// near its array rate (an M128 x N x K32 int8 MMA costs max(~63, N / 2) cycles, tools/probes/umma_probe.cu), which
+// the 3-microphone problem (N = 64) cannot reach -- see DESIGN.md 4.5.
+//
+// No reference counterpart exists for these shapes: parity is against the generalised oracle (oracle/at_oracle.c),
+// "unpinned" in the sense of DESIGN.md section 2, and against the mma.sync kernel (at_fused_imma_cta.cu).
+//
+// Work per frame: for y = 1..7 and each digit d of y, the product  (y.d plane) x [x0.h x0.l ... x(y-1).h x(y-1).l]  over
+// all K-steps fills 32 y TMEM columns.  The 14 (y, d) groups are packed into 7 passes of exactly 256 columns
+// ({7h,1h} {7l,1l} {6h,2h} {6l,2l} {5h,3h} {5l,3l} {4h,4l}), TMEM holds two passes, so the tensor core fills one slot
+// while the CUDA cores drain the other.  CTA = 17 warps, one CTA per SM, persistent, warp-specialised:
+//   warp 0       one elected lane issues the MMAs (frames and passes in order) and commits them to mbarriers;
+//   warps 1-8    prep, one channel each: loads, DC removal, <<8, window, balanced digit planes to shared memory
+//                (double-buffered frames);
+//   warps 9-16   epilogue (256 threads, two warps per TMEM lane quadrant): 16 tiles per pass in four rounds of four --
+//                tcgen05.ld 32x32b.x16, transposing scatter through shared memory, 16-term diagonal sums added into
+//                per-(pair, digit-class, lag) int32 accumulators; after the last pass the int64 recombination and the
+//                block epilogue of at_fused_common.cuh (arg-max, Gaussian re-weighting, outputs).
+#include <limits.h>
+#include <stdlib.h>
+
+#include "at_imma_common.cuh"
+#include "at_umma_common.cuh"
+
+namespace atk {
+
+template <int NBITS, int L>
+struct UmmaMGeo {
+    static constexpr int NM = 8, P = 28;
+    static constexpr int N = 1 << NBITS;
+    static constexpr int PAD = 48;                       // lag index j = s + PAD; also the left zero pad of a plane
+    static constexpr int PLANE = N + 128;                // 48 zeros, N samples, 80 zeros
+    static constexpr int KSTEPS = N / 512;               // one MMA (K = 32 rows of 16 bytes) covers 512 samples
+    static constexpr int FRAME = 2 * NM * PLANE;         // planes [channel][h, l]
+    static constexpr int NJ = 96;
+    static constexpr int ZP = 144;                       // words per (tile, phase) column of the transposing scratch
+    static constexpr int TCOLS = 256;                    // TMEM columns per pass
+    static constexpr int PASSES = 7;
+    static constexpr int EPI_THREADS = 256;
+    static_assert(Geo<NBITS, L>::PADL == PAD && Geo<NBITS, L>::NLAGS_PAD == NJ, "curve layout of the block epilogue");
+    static_assert(PAD + L + 15 < 128, "lag window must fit the 128-row tile");
+    static_assert(127 + 16 * (N / 16 - 1) + 15 < PLANE, "A operand reads stay inside a plane buffer");
+};
+
+template <int NBITS, int L>
+struct UmmaMSmem {
+    using G = UmmaMGeo<NBITS, L>;
+    alignas(128) uint8_t planes[2][G::FRAME];
+    union {                                              // the curves are built when the scratch is dead
+        int z[4][16][G::ZP];                             // [tile of the round][phase][row - phase + 15]
+        EpiSmem<G::NM, NBITS, L> epi;
+    };
+    alignas(16) int acc[G::P][3][G::NJ];                 // diagonal sums by digit class: hh, hl + lh, ll
+    alignas(16) uint32_t win2[G::N];
+    float gauss[2 * L + 1];
+    alignas(8) uint64_t full[2], empty[2], ready[2], sfree[2];
+    uint32_t tmem_base;
+};
+
+// pass g holds two (y, digit) groups: group 0 at column 0, group 1 at column 32 * y0
+__device__ __forceinline__ constexpr int pass_y(int g, int k) { return k == 0 ? 7 - (g >> 1) : (g == 6 ? 4 : 1 + (g >> 1)); }
+__device__ __forceinline__ constexpr int pass_d(int g, int k) { return g == 6 ? k : (g & 1); }
+
+template <int NBITS, int L>
+__global__ void __launch_bounds__(544, 1) at_fused_umma_m_kernel(const AtFusedParams p)
+{
+    using G = UmmaMGeo<NBITS, L>;
+    using S = UmmaMSmem<NBITS, L>;
+    constexpr int N = G::N, PAD = G::PAD, PLANE = G::PLANE, NM = G::NM, P = G::P, NJ = G::NJ;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    S &s = *reinterpret_cast<S *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- one-time CTA set-up
+    for (int i = tid; i < (int)(sizeof(s.planes) / 16); i += 544)
+        reinterpret_cast<uint4 *>(&s.planes[0][0])[i] = make_uint4(0, 0, 0, 0);
+    imma_win_fill(s.win2, p.window, N, tid, 544);
+    for (int i = tid; i < 2 * L + 1; i += 544) s.gauss[i] = p.gauss[i];
+    if (tid == 0) {
+        for (int k = 0; k < 2; k++) {
+            mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], 8);
+            mbar_init(&s.ready[k], NM); mbar_init(&s.sfree[k], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s.tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const unsigned long long nf = p.n_frames, gstride = gridDim.x;
+    // frames of this CTA: f = blockIdx.x + gridDim.x * i; frame i uses plane buffer i & 1; its pass g is pass number
+    // 7 i + g of the CTA and uses TMEM slot (7 i + g) & 1.  Every mbarrier is waited on in phase order.
+
+    if (warp == 0) {
+        // =================================================================== MMA issue
+        constexpr uint32_t LBO = (128u >> 4) << 16;
+        constexpr uint32_t HI_A = (16u >> 4) | 0x4000u, HI_B = ((uint32_t)PLANE >> 4) | 0x4000u;
+        for (unsigned long long i = 0;; i++) {
+            if (blockIdx.x + gstride * i >= nf) break;
+            const unsigned b = (unsigned)(i & 1);
+            mbar_wait(&s.ready[b], (unsigned)(i >> 1) & 1);
+            const uint32_t b16 = (smem_u32(&s.planes[b][0]) >> 4) + LBO;          // start-address field of plane 0 (x0.h)
+#pragma unroll 1
+            for (int g = 0; g < G::PASSES; g++) {
+                const unsigned long long gp = 7 * i + g;
+                const unsigned slot = (unsigned)(gp & 1), u = (unsigned)(gp >> 1);
+                if (u >= 1) mbar_wait(&s.empty[slot], (u - 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t cb = tmem + slot * G::TCOLS;
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const int y = pass_y(g, k), d = pass_d(g, k);
+                        const uint32_t col = k == 0 ? 0u : 32u * (uint32_t)pass_y(g, 0);
+                        const uint32_t idesc = umma_idesc(32 * y);
+                        const uint32_t a0 = b16 + (uint32_t)((2 * y + d) * (PLANE >> 4)), x0 = b16 + (PAD >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < G::KSTEPS; kk++)
+                            umma_i8_lohi(cb + col, a0 + 32 * kk, HI_A, x0 + 32 * kk, HI_B, idesc, kk ? 1u : 0u);
+                    }
+                    umma_commit(&s.full[slot]);
+                    if (g == G::PASSES - 1) umma_commit(&s.sfree[b]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp <= NM) {
+        // =================================================================== prep warps, one channel each
+        const int ch = warp - 1;
+        constexpr int Q = N / 512;
+        for (unsigned long long i = 0;; i++) {
+            const unsigned long long f = blockIdx.x + gstride * i;
+            if (f >= nf) break;
+            const unsigned b = (unsigned)(i & 1), v = (unsigned)(i >> 1);
+            uint8_t *const ph = &s.planes[b][(2 * ch) * PLANE], *const pl = ph + PLANE;
+            const uint8_t *src = p.adc + (f * NM + ch) * (unsigned long long)N;
+            const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
+            uint4 raw[Q];
+            unsigned sum = 0;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const uint4 x = ldg_stream(src + q * 512 + lane * 16);
+                raw[q] = x;
+                sum = __dp4a(x.x, 0x01010101u, sum); sum = __dp4a(x.y, 0x01010101u, sum);
+                sum = __dp4a(x.z, 0x01010101u, sum); sum = __dp4a(x.w, 0x01010101u, sum);
+            }
+            sum = __reduce_add_sync(0xffffffffu, sum);
+            const int mean = (int)(sum >> NBITS);                       // rolling_buffer.c:48-64
+            {   // this channel of the next frame -> L1/L2
+                const unsigned long long fn = f + gstride;
+                if (fn < nf && lane * 128 < N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.adc + (fn * NM + ch) * (unsigned long long)N + lane * 128));
+            }
+            if (v >= 1) mbar_wait(&s.sfree[b], (v - 1) & 1);            // the tensor core is done with frame i - 2
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const int j0 = q * 512 + lane * 16;
+                const uint32_t rw[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+                if ((head & 15) == 0) {
+                    const int i0 = (j0 - head) & (N - 1);
+                    uint32_t hi[4], lo[4];
+                    umma_prep16(rw, mean, s.win2, i0, hi, lo);
+                    *reinterpret_cast<uint4 *>(ph + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(pl + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const int ii = (j0 + e - head) & (N - 1);
+                        const int q24 = imma_prep1(rw[e >> 2] >> (8 * (e & 3)), mean, s.win2, ii) + 0x8000;
+                        ph[PAD + ii] = (uint8_t)(q24 >> 16); pl[PAD + ii] = (uint8_t)((q24 >> 8) ^ 0x80);
+                    }
+                }
+            }
+            if (p.power) {   // rolling_buffer.c:68-70
+                long long acc = 0;
+                for (int k = lane; k < N; k += 32) { const int dv = (int)src[k] - mean; acc += (long long)dv * dv; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) p.power[f * NM + ch] = acc;
+            }
+            __syncwarp();
+            if (p.windowed)
+                for (int ii = lane; ii < N; ii += 32)
+                    p.windowed[(f * NM + ch) * (unsigned long long)N + ii] =
+                        (int16_t)((int)(signed char)ph[PAD + ii] * 256 + (int)(signed char)pl[PAD + ii]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.ready[b]);
+        }
+    } else {
+        // =================================================================== epilogue group (256 threads)
+        const int et = tid - 32 * (NM + 1), wq = warp & 3, half = (warp - (NM + 1)) >> 2, m = wq * 32 + lane;
+        int *const accf = &s.acc[0][0][0];
+        for (unsigned long long i = 0;; i++) {
+            const unsigned long long f = blockIdx.x + gstride * i;
+            if (f >= nf) break;
+            for (int k = et; k < P * 3 * NJ; k += G::EPI_THREADS) accf[k] = 0;
+            named_bar(1, G::EPI_THREADS);
+#pragma unroll 1
+            for (int g = 0; g < G::PASSES; g++) {
+                const unsigned long long gp = 7 * i + g;
+                const unsigned slot = (unsigned)(gp & 1), u = (unsigned)(gp >> 1);
+                mbar_wait(&s.full[slot], u & 1);
+                tc_fence_after();
+                const int y0 = pass_y(g, 0), y1 = pass_y(g, 1), d0 = pass_d(g, 0), d1 = pass_d(g, 1);
+                const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + slot * G::TCOLS;
+#pragma unroll 1
+                for (int r = 0; r < 4; r++) {
+                    // this warp moves tiles 4r + 2 half and 4r + 2 half + 1 of its lane quadrant into the scratch
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        uint32_t t[16];
+                        tmem_ld16(ta + 16 * (4 * r + 2 * half + e), t);
+                        tmem_ld_wait();
+                        int *const zp = &s.z[2 * half + e][0][m + 15];
+#pragma unroll
+                        for (int ph = 0; ph < 16; ph++) zp[ph * G::ZP - ph] = (int)t[ph];
+                    }
+                    if (r == 3) {          // the pass is out of TMEM
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&s.empty[slot]);
+                    }
+                    named_bar(1, G::EPI_THREADS);
+                    // diagonal sums of the four tiles: 384 (tile, lag) items
+                    for (int item = et; item < 4 * NJ; item += G::EPI_THREADS) {
+                        const int k = item / NJ, j = item % NJ;
+                        const int tile = 4 * r + k;                   // tile = 16 columns: x channel tile / 2, x digit tile % 2
+                        const int grp = tile >= 2 * y0 ? 1 : 0;
+                        const int tx = grp ? tile - 2 * y0 : tile, x = tx >> 1, xd = tx & 1;
+                        const int y = grp ? y1 : y0, cls = (grp ? d1 : d0) + xd;      // hh = 0, hl / lh = 1, ll = 2
+                        const int pr = x * NM - x * (x + 1) / 2 + (y - x - 1);          // pair (x, y), x < y
+                        const int *zr = &s.z[k][0][j + 15];
+                        int sum = 0;
+#pragma unroll
+                        for (int ph = 0; ph < 16; ph++) sum += zr[ph * G::ZP];
+                        s.acc[pr][cls][j] += sum;
+                    }
+                    named_bar(1, G::EPI_THREADS);
+                }
+            }
+            // int64 recombination (the scratch is dead: its bytes now hold the curves), then the block epilogue
+            for (int k = et; k < P * NJ; k += G::EPI_THREADS) {
+                const int pr = k / NJ, j = k % NJ;
+                s.epi.curve[pr][j] = 65536LL * s.acc[pr][0][j] + 256LL * s.acc[pr][1][j] + (long long)s.acc[pr][2][j];
+            }
+            named_bar(1, G::EPI_THREADS);
+            epilogue<NM, NBITS, L, G::EPI_THREADS, 1>(s.epi, s.gauss, p, f, et);
+            named_bar(1, G::EPI_THREADS);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+}
+
+template <int NBITS, int L>
+static cudaError_t launch_umma_m(const AtFusedParams &p, int sm_count, cudaStream_t st)
+{
+    auto kern = at_fused_umma_m_kernel<NBITS, L>;
+    const int smem = (int)sizeof(UmmaMSmem<NBITS, L>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    unsigned long long grid = (unsigned long long)sm_count;
+    if (grid > p.n_frames) grid = p.n_frames;
+    if (grid == 0) return cudaSuccess;
+    kern<<<(unsigned)grid, 544, smem, st>>>(p);
+    at_count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace atk
+
+bool at_fused_umma_m_supports(const AtShape &sh)
+{
+    return sh.n_mics == 8 && (sh.n_bits == 10 || sh.n_bits == 12) && sh.max_shift == 46;
+}
+
+cudaError_t at_launch_fused_umma_m(const AtShape &sh, const AtFusedParams &p, int sm_count, cudaStream_t st)
+{
+    if (p.sig16 || !at_fused_umma_m_supports(sh)) return cudaErrorInvalidValue;
+    return sh.n_bits == 12 ? atk::launch_umma_m<12, 46>(p, sm_count, st) : atk::launch_umma_m<10, 46>(p, sm_count, st);
+}

@@ -59,6 +59,9 @@ bool at_fused_imma3_supports(const AtShape &shape);
 // at_fused_umma.cu -- tcgen05 (UMMA) polyphase kernel, 3 mics x 1024 samples
 cudaError_t at_launch_fused_umma(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
 bool at_fused_umma_supports(const AtShape &shape);
+// at_fused_umma_m.cu -- tcgen05 (UMMA) kernel for 8-microphone arrays, 1024 / 4096 samples
+cudaError_t at_launch_fused_umma_m(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
+bool at_fused_umma_m_supports(const AtShape &shape);
 
 // at_aux.cu -- small kernels
 cudaError_t at_launch_mics_triangle(float d_ab, float d_bc, float d_ca, int mirror, float *d_xy, cudaStream_t st);
