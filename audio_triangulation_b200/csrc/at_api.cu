@@ -324,8 +324,10 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
     p.debug_skip = dbg;
     p.n_cand = c->n_cand; p.n_cells = c->n_cells; p.half_w = c->cfg.half_w; p.half_h = c->cfg.half_h;
     p.px_per_m = c->cfg.px_per_m;
-    if (kernel == AT_KERNEL_AUTO)
-        kernel = (at_fused_imma_supports(sh) || at_fused_imma_cta_supports(sh)) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;   // IMMA_LM measured slower
+    if (kernel == AT_KERNEL_AUTO) {   // the fastest measured kernel of each shape
+        if (sh.n_mics == 8 && sh.n_bits == 12 && at_fused_umma_m_supports(sh) && !p.sig16) kernel = AT_KERNEL_UMMA;   // 2.8x the mma.sync form
+        else kernel = (at_fused_imma_supports(sh) || at_fused_imma_cta_supports(sh)) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;
+    }
     cudaError_t e;
     if (kernel == AT_KERNEL_UMMA) {
         if (p.sig16) return fail(AT_EINVAL, "UMMA kernels take ADC bytes, not prepared int16 frames");

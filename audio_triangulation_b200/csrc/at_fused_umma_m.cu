@@ -16,10 +16,12 @@
 //   warp 0       one elected lane issues the MMAs (frames and passes in order) and commits them to mbarriers;
 //   warps 1-8    prep, one channel each: loads, DC removal, <<8, window, balanced digit planes to shared memory
 //                (double-buffered frames);
-//   warps 9-16   epilogue (256 threads, two warps per TMEM lane quadrant): 16 tiles per pass in four rounds of four --
-//                tcgen05.ld 32x32b.x16, transposing scatter through shared memory, 16-term diagonal sums added into
-//                per-(pair, digit-class, lag) int32 accumulators; after the last pass the int64 recombination and the
-//                block epilogue of at_fused_common.cuh (arg-max, Gaussian re-weighting, outputs).
+//   warps 9-16   epilogue (256 threads, two warps per TMEM lane quadrant): the 16 tiles of a pass are 8 couples
+//                [y.d * x.h | y.d * x.l]; tcgen05.ld 32x32b.x16, couple folded to 256 * (y.d x.h) + (y.d x.l) (fits
+//                int32), transposing scatter through shared memory, 16-term diagonal sums in int64 added with the
+//                weight of y's digit (2^8 or 1) into the curves; after the last pass the block epilogue of
+//                at_fused_common.cuh (arg-max, Gaussian re-weighting, outputs).  The scatter is what bounds the
+//                kernel: every accumulator entry crosses shared memory once (write + read at 128 B/clk).
 #include <limits.h>
 #include <stdlib.h>
 
@@ -37,7 +39,8 @@ struct UmmaMGeo {
     static constexpr int KSTEPS = N / 512;               // one MMA (K = 32 rows of 16 bytes) covers 512 samples
     static constexpr int FRAME = 2 * NM * PLANE;         // planes [channel][h, l]
     static constexpr int NJ = 96;
-    static constexpr int ZP = 144;                       // words per (tile, phase) column of the transposing scratch
+    static constexpr int ZP = 112;                       // words per (tile, phase) column of the transposing scratch:
+                                                         // index = lag index + 15, only lag indices -15..95 are kept
     static constexpr int TCOLS = 256;                    // TMEM columns per pass
     static constexpr int PASSES = 7;
     static constexpr int EPI_THREADS = 256;
@@ -50,12 +53,10 @@ template <int NBITS, int L>
 struct UmmaMSmem {
     using G = UmmaMGeo<NBITS, L>;
     alignas(128) uint8_t planes[2][G::FRAME];
-    union {                                              // the curves are built when the scratch is dead
-        int z[4][16][G::ZP];                             // [tile of the round][phase][row - phase + 15]
-        EpiSmem<G::NM, NBITS, L> epi;
-    };
-    alignas(16) int acc[G::P][3][G::NJ];                 // diagonal sums by digit class: hh, hl + lh, ll
+    alignas(16) int z[8][16][G::ZP];                     // [couple of the pass][phase][row - phase + 15]
+    alignas(16) EpiSmem<G::NM, NBITS, L> epi;            // epi.curve accumulates the weighted diagonal sums of a frame
     alignas(16) uint32_t win2[G::N];
+    uint16_t couple_tab[G::PASSES][8];                   // (pair << 8) | weight shift (8: y.h, 0: y.l) of each couple
     float gauss[2 * L + 1];
     alignas(8) uint64_t full[2], empty[2], ready[2], sfree[2];
     uint32_t tmem_base;
@@ -80,6 +81,12 @@ __global__ void __launch_bounds__(544, 1) at_fused_umma_m_kernel(const AtFusedPa
         reinterpret_cast<uint4 *>(&s.planes[0][0])[i] = make_uint4(0, 0, 0, 0);
     imma_win_fill(s.win2, p.window, N, tid, 544);
     for (int i = tid; i < 2 * L + 1; i += 544) s.gauss[i] = p.gauss[i];
+    if (tid < G::PASSES * 8) {      // couple = 32 columns [y.d * x.h | y.d * x.l]: (y, d) of its group, x channel in order
+        const int g = tid >> 3, c = tid & 7, y0 = pass_y(g, 0);
+        const int grp = c >= y0 ? 1 : 0, x = grp ? c - y0 : c, y = pass_y(g, grp), d = pass_d(g, grp);
+        const int pr = x * NM - x * (x + 1) / 2 + (y - x - 1);            // pair (x, y), x < y
+        s.couple_tab[g][c] = (uint16_t)((pr << 8) | (d == 0 ? 8 : 0));
+    }
     if (tid == 0) {
         for (int k = 0; k < 2; k++) {
             mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], 8);
@@ -197,11 +204,11 @@ __global__ void __launch_bounds__(544, 1) at_fused_umma_m_kernel(const AtFusedPa
     } else {
         // =================================================================== epilogue group (256 threads)
         const int et = tid - 32 * (NM + 1), wq = warp & 3, half = (warp - (NM + 1)) >> 2, m = wq * 32 + lane;
-        int *const accf = &s.acc[0][0][0];
+        long long *const curvef = &s.epi.curve[0][0];
         for (unsigned long long i = 0;; i++) {
             const unsigned long long f = blockIdx.x + gstride * i;
             if (f >= nf) break;
-            for (int k = et; k < P * 3 * NJ; k += G::EPI_THREADS) accf[k] = 0;
+            for (int k = et; k < P * NJ; k += G::EPI_THREADS) curvef[k] = 0;
             named_bar(1, G::EPI_THREADS);
 #pragma unroll 1
             for (int g = 0; g < G::PASSES; g++) {
@@ -209,49 +216,44 @@ __global__ void __launch_bounds__(544, 1) at_fused_umma_m_kernel(const AtFusedPa
                 const unsigned slot = (unsigned)(gp & 1), u = (unsigned)(gp >> 1);
                 mbar_wait(&s.full[slot], u & 1);
                 tc_fence_after();
-                const int y0 = pass_y(g, 0), y1 = pass_y(g, 1), d0 = pass_d(g, 0), d1 = pass_d(g, 1);
                 const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + slot * G::TCOLS;
+                // this warp moves couples 4 half + (0..3) of its lane quadrant into the scratch, two at a time
 #pragma unroll 1
-                for (int r = 0; r < 4; r++) {
-                    // this warp moves tiles 4r + 2 half and 4r + 2 half + 1 of its lane quadrant into the scratch
+                for (int r = 0; r < 2; r++) {
+                    uint32_t t[4][16];
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        uint32_t t[16];
-                        tmem_ld16(ta + 16 * (4 * r + 2 * half + e), t);
-                        tmem_ld_wait();
-                        int *const zp = &s.z[2 * half + e][0][m + 15];
-#pragma unroll
-                        for (int ph = 0; ph < 16; ph++) zp[ph * G::ZP - ph] = (int)t[ph];
-                    }
-                    if (r == 3) {          // the pass is out of TMEM
+                    for (int e = 0; e < 4; e++) tmem_ld16(ta + 16 * (8 * half + 4 * r + e), t[e]);
+                    tmem_ld_wait();
+                    if (r == 1) {          // the pass is out of TMEM
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&s.empty[slot]);
                     }
-                    named_bar(1, G::EPI_THREADS);
-                    // diagonal sums of the four tiles: 384 (tile, lag) items
-                    for (int item = et; item < 4 * NJ; item += G::EPI_THREADS) {
-                        const int k = item / NJ, j = item % NJ;
-                        const int tile = 4 * r + k;                   // tile = 16 columns: x channel tile / 2, x digit tile % 2
-                        const int grp = tile >= 2 * y0 ? 1 : 0;
-                        const int tx = grp ? tile - 2 * y0 : tile, x = tx >> 1, xd = tx & 1;
-                        const int y = grp ? y1 : y0, cls = (grp ? d1 : d0) + xd;      // hh = 0, hl / lh = 1, ll = 2
-                        const int pr = x * NM - x * (x + 1) / 2 + (y - x - 1);          // pair (x, y), x < y
-                        const int *zr = &s.z[k][0][j + 15];
-                        int sum = 0;
 #pragma unroll
-                        for (int ph = 0; ph < 16; ph++) sum += zr[ph * G::ZP];
-                        s.acc[pr][cls][j] += sum;
+                    for (int e = 0; e < 2; e++) {
+                        int *const zp = &s.z[4 * half + 2 * r + e][0][m + 15];
+#pragma unroll
+                        for (int ph = 0; ph < 16; ph++)     // entry (m, phi): lag index m - phi; |256 a + b| < 2^31
+                            if (m - ph < NJ) zp[ph * G::ZP - ph] = 256 * (int)t[2 * e][ph] + (int)t[2 * e + 1][ph];
                     }
-                    named_bar(1, G::EPI_THREADS);
                 }
+                named_bar(1, G::EPI_THREADS);
+                // diagonal sums of the eight couples: 768 (couple, lag) items, three per thread.  The last pass {4h, 4l}
+                // holds both digits of the same pairs, so two threads can meet on one curve entry: atomic add there.
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const int item = et + G::EPI_THREADS * q, k = item / NJ, j = item - k * NJ;
+                    const int *zr = &s.z[k][0][j + 15];
+                    long long sum = 0;
+#pragma unroll
+                    for (int ph = 0; ph < 16; ph++) sum += zr[ph * G::ZP];
+                    const unsigned tt = s.couple_tab[g][k];
+                    long long *const dst = &curvef[(tt >> 8) * NJ + j];
+                    if (g == G::PASSES - 1) atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)(sum << (tt & 31)));
+                    else *dst += sum << (tt & 31);
+                }
+                named_bar(1, G::EPI_THREADS);
             }
-            // int64 recombination (the scratch is dead: its bytes now hold the curves), then the block epilogue
-            for (int k = et; k < P * NJ; k += G::EPI_THREADS) {
-                const int pr = k / NJ, j = k % NJ;
-                s.epi.curve[pr][j] = 65536LL * s.acc[pr][0][j] + 256LL * s.acc[pr][1][j] + (long long)s.acc[pr][2][j];
-            }
-            named_bar(1, G::EPI_THREADS);
             epilogue<NM, NBITS, L, G::EPI_THREADS, 1>(s.epi, s.gauss, p, f, et);
             named_bar(1, G::EPI_THREADS);
         }

@@ -346,6 +346,24 @@ def test_bounded_search_paths_are_exercised(loc, oracle):
 
 
 # ---------------------------------------------------------------- other shapes (no reference pin)
+@pytest.mark.parametrize("shape", [(8, 12, 46, 1500), (8, 10, 46, 6000)])
+def test_umma_8mic_large_batch_equals_mma_sync_kernel(shape):
+    """Many frames per CTA (TMEM slot and plane-buffer re-use, the last pass' shared atomics): the tcgen05 kernel
+    against the mma.sync CTA kernel, itself oracle-checked below.  No reference pin for 8 microphones."""
+    M, nb, Ls, F = shape
+    torch = _torch()
+    res = {}
+    for kernel in ("imma", "umma"):
+        loc = make_loc(kernel, n_mics=M, n_bits=nb, max_shift=Ls)
+        adc, heads, _ = loc.synth_device(F, flags=2, seed=5)
+        r = loc.localize_device(adc, heads, want=("lags", "raw", "corr"))
+        torch.cuda.synchronize()
+        res[kernel] = {k: v.cpu() for k, v in r.items()}
+        loc.close()
+    for k in ("lags", "raw", "corr"):
+        assert torch.equal(res["imma"][k], res["umma"][k]), k
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("shape", [(8, 12, 46, 24), (3, 10, 44, 64), (4, 10, 46, 64), (3, 12, 46, 32), (8, 10, 46, 48)])
 def test_generalised_shapes_vs_oracle(kernel, shape):
