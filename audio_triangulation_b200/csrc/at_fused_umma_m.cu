@@ -12,11 +12,11 @@
 // Work per frame: for y = 1..7 and each digit d of y, the product  (y.d plane) x [x0.h x0.l ... x(y-1).h x(y-1).l]  over
 // all K-steps fills 32 y TMEM columns.  The 14 (y, d) groups are packed into 7 passes of exactly 256 columns
 // ({7h,1h} {7l,1l} {6h,2h} {6l,2l} {5h,3h} {5l,3l} {4h,4l}), TMEM holds two passes, so the tensor core fills one slot
-// while the CUDA cores drain the other.  CTA = 17 warps, one CTA per SM, persistent, warp-specialised:
+// while the CUDA cores drain the other.  CTA = 25 warps, one CTA per SM, persistent, warp-specialised:
 //   warp 0       one elected lane issues the MMAs (frames and passes in order) and commits them to mbarriers;
 //   warps 1-8    prep, one channel each: loads, DC removal, <<8, window, balanced digit planes to shared memory
 //                (double-buffered frames);
-//   warps 9-16   epilogue (256 threads, two warps per TMEM lane quadrant): the 16 tiles of a pass are 8 couples
+//   warps 9-24   epilogue (512 threads, four warps per TMEM lane quadrant): the 16 tiles of a pass are 8 couples
 //                [y.d * x.h | y.d * x.l]; tcgen05.ld 32x32b.x16, couple folded to 256 * (y.d x.h) + (y.d x.l) (fits
 //                int32), transposing scatter through shared memory, 16-term diagonal sums in int64 added with the
 //                weight of y's digit (2^8 or 1) into the curves; after the last pass the block epilogue of
@@ -43,7 +43,8 @@ struct UmmaMGeo {
                                                          // index = lag index + 15, only lag indices -15..95 are kept
     static constexpr int TCOLS = 256;                    // TMEM columns per pass
     static constexpr int PASSES = 7;
-    static constexpr int EPI_THREADS = 256;
+    static constexpr int EPI_WARPS = 16, EPI_THREADS = 32 * EPI_WARPS;
+    static constexpr int THREADS = 32 * (1 + NM) + EPI_THREADS;   // 800
     static_assert(Geo<NBITS, L>::PADL == PAD && Geo<NBITS, L>::NLAGS_PAD == NJ, "curve layout of the block epilogue");
     static_assert(PAD + L + 15 < 128, "lag window must fit the 128-row tile");
     static_assert(127 + 16 * (N / 16 - 1) + 15 < PLANE, "A operand reads stay inside a plane buffer");
@@ -67,7 +68,7 @@ __device__ __forceinline__ constexpr int pass_y(int g, int k) { return k == 0 ? 
 __device__ __forceinline__ constexpr int pass_d(int g, int k) { return g == 6 ? k : (g & 1); }
 
 template <int NBITS, int L>
-__global__ void __launch_bounds__(544, 1) at_fused_umma_m_kernel(const AtFusedParams p)
+__global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_m_kernel(const AtFusedParams p)
 {
     using G = UmmaMGeo<NBITS, L>;
     using S = UmmaMSmem<NBITS, L>;
@@ -77,10 +78,10 @@ __global__ void __launch_bounds__(544, 1) at_fused_umma_m_kernel(const AtFusedPa
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- one-time CTA set-up
-    for (int i = tid; i < (int)(sizeof(s.planes) / 16); i += 544)
+    for (int i = tid; i < (int)(sizeof(s.planes) / 16); i += G::THREADS)
         reinterpret_cast<uint4 *>(&s.planes[0][0])[i] = make_uint4(0, 0, 0, 0);
-    imma_win_fill(s.win2, p.window, N, tid, 544);
-    for (int i = tid; i < 2 * L + 1; i += 544) s.gauss[i] = p.gauss[i];
+    imma_win_fill(s.win2, p.window, N, tid, G::THREADS);
+    for (int i = tid; i < 2 * L + 1; i += G::THREADS) s.gauss[i] = p.gauss[i];
     if (tid < G::PASSES * 8) {      // couple = 32 columns [y.d * x.h | y.d * x.l]: (y, d) of its group, x channel in order
         const int g = tid >> 3, c = tid & 7, y0 = pass_y(g, 0);
         const int grp = c >= y0 ? 1 : 0, x = grp ? c - y0 : c, y = pass_y(g, grp), d = pass_d(g, grp);
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(544, 1) at_fused_umma_m_kernel(const AtFusedPa
     }
     if (tid == 0) {
         for (int k = 0; k < 2; k++) {
-            mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], 8);
+            mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], G::EPI_WARPS);
             mbar_init(&s.ready[k], NM); mbar_init(&s.sfree[k], 1);
         }
         fence_barrier_init();
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(544, 1) at_fused_umma_m_kernel(const AtFusedPa
         }
     } else {
         // =================================================================== epilogue group (256 threads)
-        const int et = tid - 32 * (NM + 1), wq = warp & 3, half = (warp - (NM + 1)) >> 2, m = wq * 32 + lane;
+        const int et = tid - 32 * (NM + 1), wq = warp & 3, part = (warp - (NM + 1)) >> 2, m = wq * 32 + lane;
         long long *const curvef = &s.epi.curve[0][0];
         for (unsigned long long i = 0;; i++) {
             const unsigned long long f = blockIdx.x + gstride * i;
@@ -217,32 +218,30 @@ __global__ void __launch_bounds__(544, 1) at_fused_umma_m_kernel(const AtFusedPa
                 mbar_wait(&s.full[slot], u & 1);
                 tc_fence_after();
                 const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + slot * G::TCOLS;
-                // this warp moves couples 4 half + (0..3) of its lane quadrant into the scratch, two at a time
-#pragma unroll 1
-                for (int r = 0; r < 2; r++) {
+                // this warp moves couples 2 part and 2 part + 1 of its lane quadrant into the scratch
+                {
                     uint32_t t[4][16];
 #pragma unroll
-                    for (int e = 0; e < 4; e++) tmem_ld16(ta + 16 * (8 * half + 4 * r + e), t[e]);
+                    for (int e = 0; e < 4; e++) tmem_ld16(ta + 16 * (4 * part + e), t[e]);
                     tmem_ld_wait();
-                    if (r == 1) {          // the pass is out of TMEM
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&s.empty[slot]);
-                    }
+                    tc_fence_before();     // the pass is out of TMEM
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s.empty[slot]);
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        int *const zp = &s.z[4 * half + 2 * r + e][0][m + 15];
+                        int *const zp = &s.z[2 * part + e][0][m + 15];
 #pragma unroll
                         for (int ph = 0; ph < 16; ph++)     // entry (m, phi): lag index m - phi; |256 a + b| < 2^31
                             if (m - ph < NJ) zp[ph * G::ZP - ph] = 256 * (int)t[2 * e][ph] + (int)t[2 * e + 1][ph];
                     }
                 }
                 named_bar(1, G::EPI_THREADS);
-                // diagonal sums of the eight couples: 768 (couple, lag) items, three per thread.  The last pass {4h, 4l}
+                // diagonal sums of the eight couples: 768 (couple, lag) items over 512 threads.  The last pass {4h, 4l}
                 // holds both digits of the same pairs, so two threads can meet on one curve entry: atomic add there.
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
+                for (int q = 0; q < 2; q++) {
                     const int item = et + G::EPI_THREADS * q, k = item / NJ, j = item - k * NJ;
+                    if (item >= 8 * NJ) break;
                     const int *zr = &s.z[k][0][j + 15];
                     long long sum = 0;
 #pragma unroll
@@ -273,7 +272,7 @@ static cudaError_t launch_umma_m(const AtFusedParams &p, int sm_count, cudaStrea
     unsigned long long grid = (unsigned long long)sm_count;
     if (grid > p.n_frames) grid = p.n_frames;
     if (grid == 0) return cudaSuccess;
-    kern<<<(unsigned)grid, 544, smem, st>>>(p);
+    kern<<<(unsigned)grid, UmmaMGeo<NBITS, L>::THREADS, smem, st>>>(p);
     at_count_launch();
     return cudaGetLastError();
 }
