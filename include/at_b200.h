@@ -119,7 +119,8 @@ uint64_t at_get_time_us(void);
 #define AT_KERNEL_IMAD 1  /* IMAD.WIDE register-tiled direct form (integer pipe) */
 #define AT_KERNEL_IMMA 2  /* byte-split Toeplitz x Hankel int8 tensor-core form (exact) */
 #define AT_KERNEL_IMMA_LM 3 /* same, fragments via ldmatrix + delayed plane copies (fewest instructions; N = 1024) */
-#define AT_KERNEL_UMMA 4  /* polyphase Hankel form on tcgen05 (UMMA, TMEM accumulators), exact; 3 mics x 1024 samples */
+#define AT_KERNEL_UMMA 4  /* polyphase Hankel form on tcgen05 (UMMA, TMEM accumulators), exact; 3 mics x 1024 samples,
+                             8 mics x 1024 / 4096 samples (AUTO picks it for 8 x 4096) */
 
 /* layout of the optional correlation-curve output */
 #define AT_CORR_PACKED 0  /* int64 [F][pairs][2L+1] */
