@@ -364,7 +364,7 @@ def test_umma_8mic_large_batch_equals_mma_sync_kernel(shape):
         assert torch.equal(res["imma"][k], res["umma"][k]), k
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel", KERNELS + ("auto",))
 @pytest.mark.parametrize("shape", [(8, 12, 46, 24), (3, 10, 44, 64), (4, 10, 46, 64), (3, 12, 46, 32), (8, 10, 46, 48)])
 def test_generalised_shapes_vs_oracle(kernel, shape):
     M, nb, Ls, F = shape
