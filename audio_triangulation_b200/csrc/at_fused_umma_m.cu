@@ -17,8 +17,8 @@
 //   warps 1-8    prep, one channel each: loads, DC removal, <<8, window, balanced digit planes to shared memory
 //                (double-buffered frames);
 //   warps 9-24   epilogue (512 threads, four warps per TMEM lane quadrant): the 16 tiles of a pass are 8 couples
-//                [y.d * x.h | y.d * x.l]; tcgen05.ld 32x32b.x16, couple folded to 256 * (y.d x.h) + (y.d x.l) (fits
-//                int32), transposing scatter through shared memory, 16-term diagonal sums in int64 added with the
+//                [y.d * x.h | y.d * x.l]; tcgen05.ld 32x32b, couple folded to 256 * (y.d x.h) + (y.d x.l) (fits
+//                int32), transposing scatter through shared memory, 16- (or 8-) term diagonal sums in int64 added with the
 //                weight of y's digit (2^8 or 1) into the curves; after the last pass the block epilogue of
 //                at_fused_common.cuh (arg-max, Gaussian re-weighting, outputs).  The scatter is what bounds the
 //                kernel: every accumulator entry crosses shared memory once (write + read at 128 B/clk).
@@ -37,10 +37,15 @@ struct UmmaMGeo {
     static constexpr int PAD = 48;                       // lag index j = s + PAD; also the left zero pad of a plane
     static constexpr int PLANE = N + 128;                // 48 zeros, N samples, 80 zeros
     static constexpr int KSTEPS = N / 512;               // one MMA (K = 32 rows of 16 bytes) covers 512 samples
-    static constexpr int FRAME = 2 * NM * PLANE;         // planes [channel][h, l]
+    // 1024-sample frames: every plane is stored twice, the second copy advanced by 8 bytes, and both copies are
+    // accumulated into the same tiles (D2[m][phi] = D[m][phi] + D[m+8][phi+8], phi < 8, as in at_fused_umma.cu): the MMA
+    // time doubles, where it is small, and the diagonal sums -- the bound -- halve.  4096-sample frames keep one copy.
+    static constexpr int COPIES = NBITS <= 10 ? 2 : 1;
+    static constexpr int PH = 16 / COPIES;               // phases per tile the epilogue has to add up
+    static constexpr int FRAME = COPIES * 2 * NM * PLANE;    // planes [copy][channel][h, l]
     static constexpr int NJ = 96;
     static constexpr int ZP = 112;                       // words per (tile, phase) column of the transposing scratch:
-                                                         // index = lag index + 15, only lag indices -15..95 are kept
+                                                         // index = lag index + PH - 1, only lag indices < 96 are kept
     static constexpr int TCOLS = 256;                    // TMEM columns per pass
     static constexpr int PASSES = 7;
     static constexpr int EPI_WARPS = 16, EPI_THREADS = 32 * EPI_WARPS;
@@ -54,7 +59,7 @@ template <int NBITS, int L>
 struct UmmaMSmem {
     using G = UmmaMGeo<NBITS, L>;
     alignas(128) uint8_t planes[2][G::FRAME];
-    alignas(16) int z[8][16][G::ZP];                     // [couple of the pass][phase][row - phase + 15]
+    alignas(16) int z[8][G::PH][G::ZP];                  // [couple of the pass][phase][row - phase + PH - 1]
     alignas(16) EpiSmem<G::NM, NBITS, L> epi;            // epi.curve accumulates the weighted diagonal sums of a frame
     alignas(16) uint32_t win2[G::N];
     uint16_t couple_tab[G::PASSES][8];                   // (pair << 8) | weight shift (8: y.h, 0: y.l) of each couple
@@ -129,10 +134,14 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
                         const int y = pass_y(g, k), d = pass_d(g, k);
                         const uint32_t col = k == 0 ? 0u : 32u * (uint32_t)pass_y(g, 0);
                         const uint32_t idesc = umma_idesc(32 * y);
-                        const uint32_t a0 = b16 + (uint32_t)((2 * y + d) * (PLANE >> 4)), x0 = b16 + (PAD >> 4);
 #pragma unroll
-                        for (int kk = 0; kk < G::KSTEPS; kk++)
-                            umma_i8_lohi(cb + col, a0 + 32 * kk, HI_A, x0 + 32 * kk, HI_B, idesc, kk ? 1u : 0u);
+                        for (int copy = 0; copy < G::COPIES; copy++) {
+                            const uint32_t c0 = b16 + (uint32_t)(copy * 2 * NM * (PLANE >> 4));           // plane x0.h of this copy
+                            const uint32_t a0 = c0 + (uint32_t)((2 * y + d) * (PLANE >> 4)), x0 = c0 + (PAD >> 4);
+#pragma unroll
+                            for (int kk = 0; kk < G::KSTEPS; kk++)
+                                umma_i8_lohi(cb + col, a0 + 32 * kk, HI_A, x0 + 32 * kk, HI_B, idesc, (kk | copy) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&s.full[slot]);
                     if (g == G::PASSES - 1) umma_commit(&s.sfree[b]);
@@ -177,12 +186,23 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
                     umma_prep16(rw, mean, s.win2, i0, hi, lo);
                     *reinterpret_cast<uint4 *>(ph + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4 *>(pl + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    if (G::COPIES == 2) {   // second copy, advanced by 8 bytes: sample i sits at PAD - 8 + i
+                        uint8_t *const ph2 = ph + 2 * NM * PLANE, *const pl2 = ph2 + PLANE;
+                        *reinterpret_cast<uint2 *>(ph2 + PAD - 8 + i0) = make_uint2(hi[0], hi[1]);
+                        *reinterpret_cast<uint2 *>(ph2 + PAD + i0) = make_uint2(hi[2], hi[3]);
+                        *reinterpret_cast<uint2 *>(pl2 + PAD - 8 + i0) = make_uint2(lo[0], lo[1]);
+                        *reinterpret_cast<uint2 *>(pl2 + PAD + i0) = make_uint2(lo[2], lo[3]);
+                    }
                 } else {
 #pragma unroll
                     for (int e = 0; e < 16; e++) {
                         const int ii = (j0 + e - head) & (N - 1);
                         const int q24 = imma_prep1(rw[e >> 2] >> (8 * (e & 3)), mean, s.win2, ii) + 0x8000;
                         ph[PAD + ii] = (uint8_t)(q24 >> 16); pl[PAD + ii] = (uint8_t)((q24 >> 8) ^ 0x80);
+                        if (G::COPIES == 2) {
+                            ph[2 * NM * PLANE + PAD - 8 + ii] = (uint8_t)(q24 >> 16);
+                            pl[2 * NM * PLANE + PAD - 8 + ii] = (uint8_t)((q24 >> 8) ^ 0x80);
+                        }
                     }
                 }
             }
@@ -220,18 +240,21 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
                 const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + slot * G::TCOLS;
                 // this warp moves couples 2 part and 2 part + 1 of its lane quadrant into the scratch
                 {
-                    uint32_t t[4][16];
+                    uint32_t t[4][G::PH];     // with two copies only columns 0..7 of a tile are distinct
 #pragma unroll
-                    for (int e = 0; e < 4; e++) tmem_ld16(ta + 16 * (4 * part + e), t[e]);
+                    for (int e = 0; e < 4; e++) {
+                        if constexpr (G::PH == 16) tmem_ld16(ta + 16 * (4 * part + e), t[e]);
+                        else tmem_ld8(ta + 16 * (4 * part + e), t[e]);
+                    }
                     tmem_ld_wait();
                     tc_fence_before();     // the pass is out of TMEM
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&s.empty[slot]);
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        int *const zp = &s.z[2 * part + e][0][m + 15];
+                        int *const zp = &s.z[2 * part + e][0][m + G::PH - 1];
 #pragma unroll
-                        for (int ph = 0; ph < 16; ph++)     // entry (m, phi): lag index m - phi; |256 a + b| < 2^31
+                        for (int ph = 0; ph < G::PH; ph++)  // entry (m, phi): lag index m - phi; |256 a + b| < 2^31
                             if (m - ph < NJ) zp[ph * G::ZP - ph] = 256 * (int)t[2 * e][ph] + (int)t[2 * e + 1][ph];
                     }
                 }
@@ -242,10 +265,10 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
                 for (int q = 0; q < 2; q++) {
                     const int item = et + G::EPI_THREADS * q, k = item / NJ, j = item - k * NJ;
                     if (item >= 8 * NJ) break;
-                    const int *zr = &s.z[k][0][j + 15];
+                    const int *zr = &s.z[k][0][j + G::PH - 1];
                     long long sum = 0;
 #pragma unroll
-                    for (int ph = 0; ph < 16; ph++) sum += zr[ph * G::ZP];
+                    for (int ph = 0; ph < G::PH; ph++) sum += zr[ph * G::ZP];
                     const unsigned tt = s.couple_tab[g][k];
                     long long *const dst = &curvef[(tt >> 8) * NJ + j];
                     if (g == G::PASSES - 1) atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)(sum << (tt & 31)));
