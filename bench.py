@@ -32,6 +32,32 @@ WANT = ("lags", "cell", "xy")
 BYTES_OUT_PER_FRAME = 3 * 4 + 4 + 8
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the
+    end-to-end leg are allocated next to the GPU's PCIe root (matters from 4 ranks up).  Best effort; returns the node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) > 4:
+            bus = bus[-12:]                                   # nvml reports an 8-digit PCI domain, sysfs uses 4
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -151,6 +177,7 @@ def run_ours(args):
     import audio_triangulation_b200 as at
 
     rank, local_rank, world = dist_env()
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -311,7 +338,8 @@ def run_ours(args):
                            "sharding": "contiguous frame ranges, lags gathered to rank 0 over NCCL" if world > 1 else "single GPU"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * BYTES_IN_PER_FRAME,
-                        "d2h_bytes_per_step": F * BYTES_OUT_PER_FRAME, "steps": e2e_steps, "matches_device_path": e2e_ok},
+                        "d2h_bytes_per_step": F * BYTES_OUT_PER_FRAME, "steps": e2e_steps, "matches_device_path": e2e_ok,
+                        "rank0_numa_node": numa_node},
                 "roofline": roof}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own objects on the host cores
