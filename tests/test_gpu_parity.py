@@ -417,3 +417,32 @@ def test_full_batch_properties(loc, oracle):
     rot = loc.localize_device(rolled, h, want=("lags",))
     torch.cuda.synchronize()
     assert torch.equal(rot["lags"], lags["lags"][:n])
+
+
+def test_config4_batch_properties():
+    """BASELINE config 4 (8 mics x 4096 samples, 28 pairs; no reference pin) at a batch of 2^13 frames through the
+    kernel AUTO selects (tcgen05): oracle spot check, batch-split invariance and ring-rotation invariance."""
+    torch = _torch()
+    M, nb, Ls, F = 8, 12, 46, 1 << 13
+    n_s = 1 << nb
+    loc = make_loc("auto", n_mics=M, n_bits=nb, max_shift=Ls)
+    adc, _, _ = loc.synth_device(F, seed=11)
+    res = loc.localize_device(adc, None, want=("lags", "raw"))
+    torch.cuda.synchronize()
+    idx = np.concatenate([np.arange(4), np.random.default_rng(1).integers(0, F, 40), [F - 1]])
+    sel = torch.from_numpy(idx).cuda()
+    o = Oracle(n_mics=M, n_bits=nb, max_shift=Ls, lut=None).localize(adc[sel].cpu().numpy(), want_raw=True, want_cell=False, nthreads=16)
+    assert (res["lags"][sel].cpu().numpy() == o["lags"]).all()
+    assert (res["raw"][sel].cpu().numpy() == o["raw"]).all()
+    half = loc.localize_device(adc[F // 2:], None, want=("lags",))
+    torch.cuda.synchronize()
+    assert torch.equal(half["lags"], res["lags"][F // 2:])
+    n = 512
+    h = torch.randint(0, n_s, (n,), device="cuda", dtype=torch.int32)
+    ar = torch.arange(n_s, device="cuda").view(1, 1, n_s)
+    src = (ar - h.view(n, 1, 1)) % n_s
+    rolled = torch.gather(adc[:n], 2, src.expand(n, M, n_s).long()).contiguous()
+    rot = loc.localize_device(rolled, h, want=("lags",))
+    torch.cuda.synchronize()
+    assert torch.equal(rot["lags"], res["lags"][:n])
+    loc.close()
