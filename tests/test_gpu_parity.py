@@ -293,6 +293,26 @@ def test_host_api_and_sharding_match_device_api(loc):
     assert (lags == host["lags"]).all() and (cell == host["cell"]).all()
 
 
+def test_host_api_config4_tcgen05_chunks():
+    """8 mics x 4096 through at_localize_host: several chunks on both stream slots, each a launch of the tcgen05 kernel
+    (512 TMEM columns allocated and released per CTA), equal to the device API."""
+    import os
+    torch = _torch()
+    loc = make_loc("auto", n_mics=8, n_bits=12, max_shift=46)
+    F = 701
+    adc, heads, _ = loc.synth_device(F, flags=2, seed=3)
+    dev = loc.localize_device(adc, heads, want=("lags", "raw"))
+    torch.cuda.synchronize()
+    os.environ["AT_CHUNK_FRAMES"] = "150"
+    try:
+        host = loc.localize_host(adc.cpu().numpy(), heads.cpu().numpy(), want=("lags", "raw"))
+    finally:
+        del os.environ["AT_CHUNK_FRAMES"]
+    for k in ("lags", "raw"):
+        assert (host[k] == dev[k].cpu().numpy()).all(), k
+    loc.close()
+
+
 def test_edge_cases(loc):
     import audio_triangulation_b200 as at
     torch = _torch()
