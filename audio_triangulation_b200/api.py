@@ -97,9 +97,9 @@ class Localizer:
         o = L.AtOutputs()
         o.corr_layout = L.AT_CORR_STRUCT if struct_corr else L.AT_CORR_PACKED
         for k in want:
-            if k == "stats":   # int64[4] counters the kernel adds to (zeroed here when first allocated)
+            if k == "stats":   # int64[5] counters the kernel adds to (zeroed here when first allocated)
                 if k not in res:
-                    res[k] = torch.zeros(4, dtype=torch.int64, device=adc.device)
+                    res[k] = torch.zeros(5, dtype=torch.int64, device=adc.device)
             elif k not in res:
                 res[k] = torch.empty(shapes[k][0], dtype=getattr(torch, shapes[k][1]), device=adc.device)
             setattr(o, k, res[k].data_ptr())

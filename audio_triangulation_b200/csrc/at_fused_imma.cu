@@ -60,7 +60,56 @@ __device__ __forceinline__ void load_b(uint32_t (&b)[2], const uint8_t *plane_k0
     b[1] = __funnelshift_r(w1, w2, bsh);
 }
 
-template <int NBITS, int L, int WARPS, int CTAS_PER_SM, int UNROLL>
+// The k-loop.  PRODUCTS selects the digit products it accumulates: 3 = all four (12 IMMA per step), 1 = all but l.l
+// (9 per step), 2 = l.l alone (3 per step).  A fragments: four 32-bit loads per y-plane, each landing directly in its
+// fragment register.  On this GPU every ALU instruction issued next to an IMMA costs issue time, so
+// what counts is the instruction total: fusing the loads into 64-bit ones or re-using the Hankel overlap across k-steps
+// both need register moves that cost more than the loads they save.  ya_4 = ya_s + 4 comes from a kernel parameter so
+// that ptxas cannot prove two loads adjacent and fuse them.
+template <int PLANE, int UNROLL, int PRODUCTS>
+__device__ __forceinline__ void imma_kloop(int (&acc)[3][3][4], uint32_t ya_s, uint32_t ya_4, const uint8_t *xb, int bsh, int nsteps)
+{
+    constexpr bool MAIN = (PRODUCTS & 1) != 0, LL = (PRODUCTS & 2) != 0;
+#pragma unroll UNROLL
+    for (int ks = 0; ks < nsteps; ks++) {
+        const int k0 = 32 * ks;
+        uint32_t Y[4][4], Xah[2], Xal[2], Xbh[2], Xbl[2];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {          // Y[0] = b.hi, Y[1] = b.lo, Y[2] = c.hi, Y[3] = c.lo
+            if (!MAIN && !(q & 1)) continue;   // l.l alone: the hi planes are not read
+            const uint32_t off = (2 + q) * PLANE + k0;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][0]) : "r"(ya_s + off));        // row g,   k 0..3
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][2]) : "r"(ya_4 + off));        // row g,   k 4..7
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][1]) : "r"(ya_s + off + 64));   // row g+8, k 0..3
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][3]) : "r"(ya_4 + off + 64));   // row g+8, k 4..7
+        }
+        if (MAIN) load_b(Xah, xb + 0 * PLANE + k0, bsh);
+        load_b(Xal, xb + 1 * PLANE + k0, bsh);
+        if (MAIN) load_b(Xbh, xb + 2 * PLANE + k0, bsh);
+        load_b(Xbl, xb + 3 * PLANE + k0, bsh);
+        if (PRODUCTS == 3) {
+            mma_s8_s8(acc[0][0], Y[0], Xah); mma_s8_u8(acc[0][1], Y[0], Xal); mma_u8_u8(acc[0][2], Y[1], Xal);
+            mma_s8_s8(acc[1][0], Y[2], Xah); mma_s8_u8(acc[1][1], Y[2], Xal); mma_u8_u8(acc[1][2], Y[3], Xal);
+            mma_s8_s8(acc[2][0], Y[2], Xbh); mma_s8_u8(acc[2][1], Y[2], Xbl); mma_u8_u8(acc[2][2], Y[3], Xbl);
+            mma_u8_s8(acc[0][1], Y[1], Xah); mma_u8_s8(acc[1][1], Y[3], Xah); mma_u8_s8(acc[2][1], Y[3], Xbh);
+        } else if (MAIN) {
+            mma_s8_s8(acc[0][0], Y[0], Xah); mma_s8_u8(acc[0][1], Y[0], Xal);
+            mma_s8_s8(acc[1][0], Y[2], Xah); mma_s8_u8(acc[1][1], Y[2], Xal);
+            mma_s8_s8(acc[2][0], Y[2], Xbh); mma_s8_u8(acc[2][1], Y[2], Xbl);
+            mma_u8_s8(acc[0][1], Y[1], Xah); mma_u8_s8(acc[1][1], Y[3], Xah); mma_u8_s8(acc[2][1], Y[3], Xbh);
+        } else if (LL) {
+            mma_u8_u8(acc[0][2], Y[1], Xal); mma_u8_u8(acc[1][2], Y[3], Xal); mma_u8_u8(acc[2][2], Y[3], Xbl);
+        }
+    }
+}
+
+// sqrt(a * b) rounded up (a, b < 2^27): float product and approximate root, both within 2^-20, times 1 + 2^-16
+__device__ __forceinline__ float sqrt_prod_up(unsigned a, unsigned b)
+{
+    return sqrtf((float)a * (float)b) * 1.0000153f + 1.0f;
+}
+
+template <int NBITS, int L, int WARPS, int CTAS_PER_SM, int UNROLL, bool PRUNE>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(const AtFusedParams p)
 {
     using G = ImmaGeo<NBITS, L>;
@@ -85,10 +134,14 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
     const int bal = boff & ~3, bsh = (boff & 3) * 8;
     const bool extras = p.gate || p.raw || p.corr || p.cell || p.highest || p.xy || p.classes;
 
+    // the certified 9-product shortcut (below) serves requests for lags / cell / xy / gate only and needs the peak-tuple table
+    const bool prune_ok = PRUNE && p.peak_tab && !(p.raw || p.corr || p.classes || p.highest) && !p.debug_skip;
     const unsigned long long stride = (unsigned long long)gridDim.x * WARPS;
     for (unsigned long long f = (unsigned long long)blockIdx.x * WARPS + warp; f < p.n_frames; f += stride) {
         const uint8_t *src = p.adc + f * (unsigned long long)(3 * N);
         const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
+        const bool prune = prune_ok && (head & 15) == 0;
+        unsigned sl[3] = {0, 0, 0};          // sum of squared low digits of each channel (certified shortcut only)
 
         // ---- channel sums -> floor mean (rolling_buffer.c:48-64); the sum is rotation invariant
         constexpr int Q = N / 512;               // 16-byte loads per lane and channel
@@ -126,6 +179,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                     imma_prep16(rw, mean[ch], s.win2, i0, hi, lo);
                     *reinterpret_cast<uint4 *>(plane(ch, 0) + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4 *>(plane(ch, 1) + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    if (PRUNE && prune) {
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; w4++) sl[ch] = __dp4a(lo[w4], lo[w4], sl[ch]);
+                    }
                 } else {   // ring head not 16-aligned: scalar stores (rare; capture heads are arbitrary)
 #pragma unroll
                     for (int e = 0; e < 16; e++) {
@@ -136,6 +193,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                     }
                 }
             }
+            if (PRUNE && prune) sl[ch] = __reduce_add_sync(0xffffffffu, sl[ch]);
             if (p.power) {   // rolling_buffer.c:68-70: power of the DC-removed samples (9-bit differences)
                 long long acc = 0;
                 for (int k = lane; k < N; k += 32) { const int dv = (int)src[ch * N + k] - mean[ch]; acc += (long long)dv * dv; }
@@ -167,34 +225,59 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[a][b][c] = 0;
         const uint8_t *ya = pl + aoff, *xb = pl + bal;   // + (ch*2+hl)*PLANE + k0
-        // A fragments: four 32-bit loads per y-plane, each landing directly in its fragment register.
-        // On this GPU every instruction issued next to an IMMA costs issue time (legacy mma.sync holds
-        // the dispatch port), so what counts is the instruction total: fusing the loads
-        // into 64-bit ones or re-using the Hankel overlap across k-steps both need register moves that
-        // cost more than the loads they save.  "+4" comes from a kernel parameter so that ptxas cannot
-        // prove two loads adjacent and fuse them.
         const uint32_t ya_s = smem_u32(ya);
         const uint32_t ya_4 = ya_s + (uint32_t)p.opaque_four;
         const int nsteps = (p.debug_skip & 2) ? 0 : G::KSTEPS;   // profiling knob, kept out of the loop body
-#pragma unroll UNROLL
-        for (int ks = 0; ks < nsteps; ks++) {
-            const int k0 = 32 * ks;
-            uint32_t Y[4][4], Xah[2], Xal[2], Xbh[2], Xbl[2];
+        if (PRUNE && prune) {
+            // ---- certified shortcut.  corr = C9 + LL with C9 = 65536 HH + 256 (HL + LH) and, the low digits being
+            //      unsigned, 0 <= LL[s] <= sqrt(Sl_x Sl_y) =: B by Cauchy-Schwarz (Sl = sum of squared low digits of a
+            //      channel, accumulated during prep).  If C9 puts its maximum more than B above every other lag, that
+            //      lag is THE arg-max of the exact curve (no tie possible); its peak is >= C9's, so the peak-tuple
+            //      look-up applies when C9_max >= 2048.  9 instead of 12 IMMA per k-step.  Anything else -- small
+            //      gaps, other outputs, no LUT tuple -- adds the l.l product below and takes the exact path.
+            imma_kloop<PLANE, UNROLL, 1>(acc, ya_s, ya_4, xb, bsh, nsteps);
+            int b3[3];
+            bool sure = true;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t off = (2 + q) * PLANE + k0;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][0]) : "r"(ya_s + off));        // row g,   k 0..3
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][2]) : "r"(ya_4 + off));        // row g,   k 4..7
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][1]) : "r"(ya_s + off + 64));   // row g+8, k 0..3
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][3]) : "r"(ya_4 + off + 64));   // row g+8, k 4..7
+            for (int pr = 0; pr < 3; pr++) {
+                long long c9[4], key = LLONG_MIN, second = LLONG_MIN;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
+                    c9[i] = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i];
+                    const long long k = c9[i] * 128 + (127 - j);
+                    if (j >= PAD - L && j <= PAD + L && k > key) key = k;
+                }
+                key = warp_max_i64(key);
+                const int j1 = 127 - (int)(key & 127);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
+                    if (j >= PAD - L && j <= PAD + L && j != j1 && c9[i] > second) second = c9[i];
+                }
+                second = warp_max_i64(second);
+                const int xc = pr == 2 ? 1 : 0, yc = pr == 0 ? 1 : 2;
+                const long long bound = (long long)sqrt_prod_up(sl[xc], sl[yc]) + 1;
+                sure = sure && (key >> 7) - second > bound && (key >> 7) >= 2048;
+                b3[pr] = j1 - PAD;
             }
-            load_b(Xah, xb + 0 * PLANE + k0, bsh); load_b(Xal, xb + 1 * PLANE + k0, bsh);
-            load_b(Xbh, xb + 2 * PLANE + k0, bsh); load_b(Xbl, xb + 3 * PLANE + k0, bsh);
-            // Y[0] = b.hi, Y[1] = b.lo, Y[2] = c.hi, Y[3] = c.lo
-            mma_s8_s8(acc[0][0], Y[0], Xah); mma_s8_u8(acc[0][1], Y[0], Xal); mma_u8_u8(acc[0][2], Y[1], Xal);
-            mma_s8_s8(acc[1][0], Y[2], Xah); mma_s8_u8(acc[1][1], Y[2], Xal); mma_u8_u8(acc[1][2], Y[3], Xal);
-            mma_s8_s8(acc[2][0], Y[2], Xbh); mma_s8_u8(acc[2][1], Y[2], Xbl); mma_u8_u8(acc[2][2], Y[3], Xbl);
-            mma_u8_s8(acc[0][1], Y[1], Xah); mma_u8_s8(acc[1][1], Y[3], Xah); mma_u8_s8(acc[2][1], Y[3], Xbh);
+            if (sure) {
+                const int4 e = __ldg(&p.peak_tab[((b3[0] + L) * (2 * L + 1) + (b3[1] + L)) * (2 * L + 1) + (b3[2] + L)]);
+                if (e.x >= 0 || !(p.cell || p.xy)) {
+                    if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? b3[0] : (lane == 1 ? b3[1] : b3[2]);
+                    if (lane == 0) {
+                        if (p.cell) p.cell[f] = e.x;
+                        if (p.xy) reinterpret_cast<float2 *>(p.xy)[f] = make_float2(__int_as_float(e.y), __int_as_float(e.z));
+                        if (p.gate) p.gate[f] = (b3[0] * b3[0] + b3[1] * b3[1] + b3[2] * b3[2]) > 4 ? 1 : 0;   // sample_compute.h:124-134
+                        if (p.stats) { atomicAdd(&p.stats[3], 1ull); atomicAdd(&p.stats[4], 1ull); }
+                    }
+                    __syncwarp();   // planes are rewritten by the next frame
+                    continue;
+                }
+            }
+            imma_kloop<PLANE, UNROLL, 2>(acc, ya_s, ya_4, xb, bsh, nsteps);
+        } else {
+            imma_kloop<PLANE, UNROLL, 3>(acc, ya_s, ya_4, xb, bsh, nsteps);
         }
 
         __syncwarp();   // every lane is done reading the planes: their data regions now hold the curves
@@ -239,11 +322,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
     }
 }
 
-template <int NBITS, int L, int WARPS, int CTAS_PER_SM, int UNROLL = 3>
+template <int NBITS, int L, int WARPS, int CTAS_PER_SM, bool PRUNE, int UNROLL = 3>
 static cudaError_t launch_imma(const AtFusedParams &p, int sm_count, cudaStream_t st)
 {
     using S = ImmaSmem<NBITS, L, WARPS>;
-    auto kern = at_fused_imma_kernel<NBITS, L, WARPS, CTAS_PER_SM, UNROLL>;
+    auto kern = at_fused_imma_kernel<NBITS, L, WARPS, CTAS_PER_SM, UNROLL, PRUNE>;
     const int smem = (int)sizeof(S);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -272,9 +355,11 @@ cudaError_t at_launch_fused_imma(const AtShape &sh, const AtFusedParams &p, int 
 {
     if (p.sig16 || sh.n_mics != 3) return cudaErrorInvalidValue;
     if (sh.n_bits == 10 && sh.max_shift == 46) {
-        return atk::launch_imma<10, 46, 4, 4>(p, sm_count, st);   // k-loop unrolled by 3: 11 and 33 measured 7-12 % slower
+        static const int prune = getenv("AT_IMMA_PRUNE") ? atoi(getenv("AT_IMMA_PRUNE")) : 1;   // 0: always all twelve products
+        // k-loop unrolled by 3: 11 and 33 measured 7-12 % slower
+        return prune ? atk::launch_imma<10, 46, 4, 4, true>(p, sm_count, st) : atk::launch_imma<10, 46, 4, 4, false>(p, sm_count, st);
     }
-    if (sh.n_bits == 10 && sh.max_shift == 44) return atk::launch_imma<10, 44, 4, 4>(p, sm_count, st);
-    if (sh.n_bits == 12 && sh.max_shift == 46) return atk::launch_imma<12, 46, 7, 1>(p, sm_count, st);   // 7 warps x 25.5 KB of planes fill the SM
+    if (sh.n_bits == 10 && sh.max_shift == 44) return atk::launch_imma<10, 44, 4, 4, true>(p, sm_count, st);
+    if (sh.n_bits == 12 && sh.max_shift == 46) return atk::launch_imma<12, 46, 7, 1, false>(p, sm_count, st);   // 7 warps x 25.5 KB of planes fill the SM
     return cudaErrorInvalidValue;
 }

@@ -34,7 +34,7 @@ struct AtFusedParams {
     const float2 *cell_xy;   // [n_cells] plane coordinates of each cell (vga_heatmap.h:52-53), built on the device
     // 3-pair arrays only: direct table over (i0, i1, i2) -> {first row-major cell of that LUT tuple or -1, x, y, 0}
     const int4 *peak_tab;    // [NL][NL][NL]
-    unsigned long long *stats; // optional [4]: frames resolved by the first box / a wider box / the full scan / the direct tuple look-up
+    unsigned long long *stats; // optional [5]: frames resolved by the first box / a wider box / the full scan / the direct tuple look-up; [4]: lags certified without the l.l product
     int32_t n_cand, n_cells, half_w, half_h;
     int32_t opaque_four;     // always 4; see at_fused_imma.cu
     int32_t debug_skip;      // profiling knob (env AT_DEBUG_SKIP): bit0 skip prep, bit1 skip MMA loop, bit2 skip epilogue

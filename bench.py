@@ -249,9 +249,10 @@ def run_ours(args):
         st = loc.localize_device(adc, None, want=WANT + ("stats",))["stats"]
         torch.cuda.synchronize(dev)
         st = st.cpu().numpy().astype(float)
-        if st.sum() > 0:
-            search = {"peak_tuple_lookup": st[3] / st.sum(), "first_box": st[0] / st.sum(), "widened_box": st[1] / st.sum(),
-                      "full_scan": st[2] / st.sum()}
+        if st[:4].sum() > 0:
+            tot = st[:4].sum()
+            search = {"peak_tuple_lookup": st[3] / tot, "first_box": st[0] / tot, "widened_box": st[1] / tot,
+                      "full_scan": st[2] / tot, "lags_certified_without_ll_product": st[4] / tot}
     except Exception:
         pass
 

@@ -174,9 +174,10 @@ typedef struct at_outputs {
     uint8_t *classes;   /* [F][cells] colour class per cell (ref: vga_heatmap.h:111-126) */
     int16_t *windowed;  /* [F][mics][N] frames after DC removal, <<8 and window (debug/parity) */
     int64_t *power;     /* [F][mics] buffer_t.power after DC removal (ref: rolling_buffer.c:68-70) */
-    uint64_t *stats;    /* device API only, [4] counters ADDED to: frames whose likelihood maximum was settled by
+    uint64_t *stats;    /* device API only, [5] counters ADDED to: frames whose likelihood maximum was settled by
                            the first bounded box / a widened box / the full tuple scan / the direct look-up of the
-                           tuple (best_ab, best_ac, best_bc) in the LUT (diagnostics) */
+                           tuple (best_ab, best_ac, best_bc) in the LUT; [4] = frames (a subset of [3]) whose lags
+                           were certified without the l.l digit product (diagnostics) */
 } at_outputs;
 
 /* The whole per-frame path, sample_compute.h:104-122 (+ the likelihood arg-max), for n_frames

@@ -362,7 +362,8 @@ def test_bounded_search_paths_are_exercised(loc, oracle):
     o = oracle.localize(adc, want_corr=False, nthreads=8)
     assert (r["cell"].cpu().numpy() == o["cell"]).all() and (r["highest"].cpu().numpy() == o["highest"]).all()
     st = r["stats"].cpu().numpy()
-    assert st.sum() == adc.shape[0] and st[3] > 0 and st[2] > 0 and st[0] + st[1] > 0, st   # look-up, a bounded box and the full scan all used
+    assert st[:4].sum() == adc.shape[0] and st[3] > 0 and st[2] > 0 and st[0] + st[1] > 0, st   # look-up, a bounded box and the full scan all used
+    assert 0 < st[4] <= st[3], st                                                # some lags certified without the l.l product
 
 
 # ---------------------------------------------------------------- other shapes (no reference pin)

@@ -17,4 +17,4 @@ for want in (("lags",), ("lags", "cell", "xy")):
     print("want=%-22s %.3f ms  %.1f Mframes/s  (skip=%s)" % ("+".join(want), ms, F / ms / 1e3, os.environ.get("AT_DEBUG_SKIP", "0")))
 st = loc.localize_device(adc, want=("lags", "cell", "xy", "stats"))["stats"]
 torch.cuda.synchronize()
-print("search routes [first box, widened, full scan, peak-tuple look-up]:", st.cpu().tolist())
+print("search routes [first box, widened, full scan, peak-tuple look-up, of which certified without l.l]:", st.cpu().tolist())
