@@ -66,7 +66,7 @@ __device__ __forceinline__ void load_b(uint32_t (&b)[2], const uint8_t *plane_k0
 // what counts is the instruction total: fusing the loads into 64-bit ones or re-using the Hankel overlap across k-steps
 // both need register moves that cost more than the loads they save.  ya_4 = ya_s + 4 comes from a kernel parameter so
 // that ptxas cannot prove two loads adjacent and fuse them.
-template <int PLANE, int UNROLL, int PRODUCTS>
+template <int PLANE, int UNROLL, int PRODUCTS, int ROW2>     // ROW2: byte distance between the data of MMA rows g and g+8
 __device__ __forceinline__ void imma_kloop(int (&acc)[3][3][4], uint32_t ya_s, uint32_t ya_4, const uint8_t *xb, int bsh, int nsteps)
 {
     constexpr bool MAIN = (PRODUCTS & 1) != 0, LL = (PRODUCTS & 2) != 0;
@@ -80,8 +80,8 @@ __device__ __forceinline__ void imma_kloop(int (&acc)[3][3][4], uint32_t ya_s, u
             const uint32_t off = (2 + q) * PLANE + k0;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][0]) : "r"(ya_s + off));        // row g,   k 0..3
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][2]) : "r"(ya_4 + off));        // row g,   k 4..7
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][1]) : "r"(ya_s + off + 64));   // row g+8, k 0..3
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][3]) : "r"(ya_4 + off + 64));   // row g+8, k 4..7
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][1]) : "r"(ya_s + off + ROW2));   // row g+8, k 0..3
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][3]) : "r"(ya_4 + off + ROW2));   // row g+8, k 4..7
         }
         if (MAIN) load_b(Xah, xb + 0 * PLANE + k0, bsh);
         load_b(Xal, xb + 1 * PLANE + k0, bsh);
@@ -101,6 +101,60 @@ __device__ __forceinline__ void imma_kloop(int (&acc)[3][3][4], uint32_t ya_s, u
             mma_u8_u8(acc[0][2], Y[1], Xal); mma_u8_u8(acc[1][2], Y[3], Xal); mma_u8_u8(acc[2][2], Y[3], Xbl);
         }
     }
+}
+
+// The nine-product loop with the Hankel overlap re-used and no register moves.  Every step loads ONE new 8-byte block
+// per plane into the half of the fragment quad whose data just expired; on odd steps the tile therefore has its row
+// halves exchanged and the product goes to a second accumulator set, folded back after the loop (c ^ 2 exchanges the
+// rows of a fragment).  20 instead of 28 shared-memory wavefronts per step: with 9 IMMA per step the loop is bound by
+// the shared-memory data pipe, not by the tensor pipe (profiles/r1_kloop_experiments.md).
+template <int PLANE, int KSTEPS>
+__device__ __forceinline__ void imma_kloop_reuse(int (&acc)[3][3][4], uint32_t ya_s, uint32_t ya_4, const uint8_t *xb, int bsh, int nsteps)
+{
+    static_assert(KSTEPS % 2 == 1, "schedule: one whole tile, then pairs of steps");
+    int accS[3][2][4];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) accS[a][b][c] = 0;
+    uint32_t Y[4][4];
+    auto load_half = [&](int slot, int kb) {   // slot 0: regs 0,2 (MMA row g); slot 1: regs 1,3 (MMA row g+8)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t off = (2 + q) * PLANE + kb;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][slot]) : "r"(ya_s + off));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Y[q][slot + 2]) : "r"(ya_4 + off));
+        }
+    };
+    auto mma_step = [&](int (&h0)[4], int (&m0)[4], int (&h1)[4], int (&m1)[4], int (&h2)[4], int (&m2)[4], int k0) {
+        uint32_t Xah[2], Xal[2], Xbh[2], Xbl[2];
+        load_b(Xah, xb + 0 * PLANE + k0, bsh); load_b(Xal, xb + 1 * PLANE + k0, bsh);
+        load_b(Xbh, xb + 2 * PLANE + k0, bsh); load_b(Xbl, xb + 3 * PLANE + k0, bsh);
+        mma_s8_s8(h0, Y[0], Xah); mma_s8_u8(m0, Y[0], Xal);
+        mma_s8_s8(h1, Y[2], Xah); mma_s8_u8(m1, Y[2], Xal);
+        mma_s8_s8(h2, Y[2], Xbh); mma_s8_u8(m2, Y[2], Xbl);
+        mma_u8_s8(m0, Y[1], Xah); mma_u8_s8(m1, Y[3], Xah); mma_u8_s8(m2, Y[3], Xbh);
+    };
+    if (nsteps) {
+        load_half(0, 0); load_half(1, 32);
+        mma_step(acc[0][0], acc[0][1], acc[1][0], acc[1][1], acc[2][0], acc[2][1], 0);
+#pragma unroll 2
+        for (int s = 1; s < KSTEPS; s += 2) {
+            const int k0 = 32 * s;
+            load_half(0, k0 + 32);        // block s+1 into the half that held block s-1: rows exchanged
+            mma_step(accS[0][0], accS[0][1], accS[1][0], accS[1][1], accS[2][0], accS[2][1], k0);
+            load_half(1, k0 + 64);        // block s+2 into the half that held block s: rows in order again
+            mma_step(acc[0][0], acc[0][1], acc[1][0], acc[1][1], acc[2][0], acc[2][1], k0 + 32);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[a][b][c] += accS[a][b][c ^ 2];
 }
 
 // sqrt(a * b) rounded up (a, b < 2^27): float product and approximate root, both within 2^-20, times 1 + 2^-16
@@ -129,7 +183,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
 
     uint8_t *const pl = &s.plane[warp][0][0][0];
     auto plane = [&](int ch, int hl) -> uint8_t * { return pl + (ch * 2 + hl) * PLANE; };
-    const int aoff = 8 * t + 8 * g;                 // A: plane index of (row g, k = 8t) at k0 = 0
+    // MMA rows (g, g+8) carry the lag rows (g, g+8) -- or, in the kernel with the certified shortcut, (rho, rho+4) with
+    // rho = g + 4 (g / 4): 32 bytes = one k-step apart, so that the data of MMA row g+8 at step s is the data of MMA row g
+    // at step s+1 (imma_kloop_reuse).  The plain loop is 4 % faster with the first mapping, hence both.
+    const int row_lo = PRUNE ? g + 4 * (g >> 2) : g, row_hi = PRUNE ? row_lo + 4 : g + 8;
+    const int aoff = 8 * t + 8 * row_lo;            // A: plane index of (MMA row g, k = 8t) at k0 = 0
     const int boff = 8 * t - g + PAD;               // B: plane index of (k = 8t, column g)
     const int bal = boff & ~3, bsh = (boff & 3) * 8;
     const bool extras = p.gate || p.raw || p.corr || p.cell || p.highest || p.xy || p.classes;
@@ -235,7 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
             //      lag is THE arg-max of the exact curve (no tie possible); its peak is >= C9's, so the peak-tuple
             //      look-up applies when C9_max >= 2048.  9 instead of 12 IMMA per k-step.  Anything else -- small
             //      gaps, other outputs, no LUT tuple -- adds the l.l product below and takes the exact path.
-            imma_kloop<PLANE, UNROLL, 1>(acc, ya_s, ya_4, xb, bsh, nsteps);
+            imma_kloop_reuse<PLANE, G::KSTEPS>(acc, ya_s, ya_4, xb, bsh, nsteps);
             int b3[3];
             bool sure = true;
 #pragma unroll
@@ -243,7 +301,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                 long long c9[4], key = LLONG_MIN, second = LLONG_MIN;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
+                    const int j = 8 * ((i >> 1) ? row_hi : row_lo) + 2 * t + (i & 1);
                     c9[i] = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i];
                     const long long k = c9[i] * 128 + (127 - j);
                     if (j >= PAD - L && j <= PAD + L && k > key) key = k;
@@ -252,7 +310,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                 const int j1 = 127 - (int)(key & 127);
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
+                    const int j = 8 * ((i >> 1) ? row_hi : row_lo) + 2 * t + (i & 1);
                     if (j >= PAD - L && j <= PAD + L && j != j1 && c9[i] > second) second = c9[i];
                 }
                 second = warp_max_i64(second);
@@ -275,9 +333,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                     continue;
                 }
             }
-            imma_kloop<PLANE, UNROLL, 2>(acc, ya_s, ya_4, xb, bsh, nsteps);
+            imma_kloop<PLANE, UNROLL, 2, 32>(acc, ya_s, ya_4, xb, bsh, nsteps);
         } else {
-            imma_kloop<PLANE, UNROLL, 3>(acc, ya_s, ya_4, xb, bsh, nsteps);
+            imma_kloop<PLANE, UNROLL, 3, PRUNE ? 32 : 64>(acc, ya_s, ya_4, xb, bsh, nsteps);
         }
 
         __syncwarp();   // every lane is done reading the planes: their data regions now hold the curves
@@ -292,7 +350,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
             long long key = LLONG_MIN;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
+                const int j = 8 * ((i >> 1) ? row_hi : row_lo) + 2 * t + (i & 1);
                 const long long v = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i] + (long long)acc[pr][2][i];
                 const long long k = v * 128 + (127 - j);
                 if (j >= PAD - L && j <= PAD + L && k > key) key = k;
@@ -311,7 +369,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
             for (int pr = 0; pr < 3; pr++)
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int j = 8 * (g + 8 * (i >> 1)) + 2 * t + (i & 1);
+                    const int j = 8 * ((i >> 1) ? row_hi : row_lo) + 2 * t + (i & 1);
                     if (j < G::NJ)
                         curve_base[pr * CSTRIDE + j] = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i] + (long long)acc[pr][2][i];
                 }
@@ -355,11 +413,16 @@ cudaError_t at_launch_fused_imma(const AtShape &sh, const AtFusedParams &p, int 
 {
     if (p.sig16 || sh.n_mics != 3) return cudaErrorInvalidValue;
     if (sh.n_bits == 10 && sh.max_shift == 46) {
-        static const int prune = getenv("AT_IMMA_PRUNE") ? atoi(getenv("AT_IMMA_PRUNE")) : 1;   // 0: always all twelve products
+        static const int prune_env = getenv("AT_IMMA_PRUNE") ? atoi(getenv("AT_IMMA_PRUNE")) : 1;   // 0: always all twelve products
+        // the certified nine-product shortcut serves lags / cell / xy / gate; whole curves go through the plain kernel
+        const bool prune = prune_env && p.peak_tab && !(p.raw || p.corr || p.classes || p.highest);
         // k-loop unrolled by 3: 11 and 33 measured 7-12 % slower
         return prune ? atk::launch_imma<10, 46, 4, 4, true>(p, sm_count, st) : atk::launch_imma<10, 46, 4, 4, false>(p, sm_count, st);
     }
-    if (sh.n_bits == 10 && sh.max_shift == 44) return atk::launch_imma<10, 44, 4, 4, true>(p, sm_count, st);
+    if (sh.n_bits == 10 && sh.max_shift == 44) {
+        const bool prune = p.peak_tab && !(p.raw || p.corr || p.classes || p.highest);
+        return prune ? atk::launch_imma<10, 44, 4, 4, true>(p, sm_count, st) : atk::launch_imma<10, 44, 4, 4, false>(p, sm_count, st);
+    }
     if (sh.n_bits == 12 && sh.max_shift == 46) return atk::launch_imma<12, 46, 7, 1, false>(p, sm_count, st);   // 7 warps x 25.5 KB of planes fill the SM
     return cudaErrorInvalidValue;
 }
