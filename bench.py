@@ -304,20 +304,24 @@ def run_ours(args):
     if rank == 0:
         # The auto / imma kernel computes the 279,210 int16 MACs of a frame as 4 x 279,210 int8 MACs on the
         # tensor cores (byte-split Toeplitz x Hankel tiles); padded to whole 16x8x32 tiles that is 396 IMMA =
-        # 1,622,016 int8 MACs issued.  Peak = legacy mma.sync int8 rate measured live on this GPU
+        # 1,622,016 int8 MACs -- of which the l.l digit product (99 IMMA) is issued only for the frames whose
+        # arg-max the other nine products cannot certify.  Peak = legacy mma.sync int8 rate measured live on this GPU
         # (MEASURED_PEAKS.json carries no int8 figure; its bf16 number is the tcgen05 path this kernel cannot use,
         # see DESIGN.md).  The imad kernel is measured against the IMAD.WIDE chain rate instead.
         imma = kernel_used in ("auto", "imma", "imma_lm")
         peak_name = "imma_s8" if imma else "imad_wide"
         peak = ubench.get(peak_name, {}).get("gops", 0.0) / 1e3
         per_frame = MAC_PER_FRAME * (4 if imma else 1)
+        certified = (search or {}).get("lags_certified_without_ll_product", 0.0) if kernel_used in ("auto", "imma") else 0.0
+        issued_per_frame = 4096 * 33 * (9 + 3 * (1.0 - certified))          # int8 MACs on the tensor pipe per frame
         achieved = per_frame * F / (kern_ms * 1e-3) / 1e12
         roof = {"bound": "tensor" if imma else "int-pipe",
                 "achieved": achieved, "peak": peak,
                 "unit": "T int8-MAC/s (4 per int16 MAC, useful lags only)" if imma else "T int16-MAC/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
                 "peak_source": "measured live: at_microbench(%s) on this GPU" % peak_name,
-                "issued_frac": (achieved * 1622016 / per_frame / peak) if (imma and peak) else None,
+                "issued_frac": (achieved * issued_per_frame / per_frame / peak) if (imma and peak) else None,
+                "issued_int8_mac_per_frame": issued_per_frame if imma else None,
                 # the same work expressed against the INTEGER-pipe roofline the direct form would have:
                 # 279,210 int16 MAC per frame vs the measured one-instruction-per-MAC rates of this GPU
                 "int16_tmac_per_s": MAC_PER_FRAME * F / (kern_ms * 1e-3) / 1e12,
