@@ -21,6 +21,12 @@
 // per-column byte offset), then finds the three first-max lags with REDUX reductions and, if asked,
 // runs the warp-scope epilogue (Gaussian re-weighting, bounded likelihood search).  No block-level
 // synchronisation after start-up.  Why the loop looks the way it does: DESIGN.md section 4.1.
+//
+// Two instantiations per shape.  PRUNE = false is the kernel just described; it serves requests for whole curves
+// (raw / corr / classes / highest).  PRUNE = true serves lags / cell / xy / gate: it first runs nine of the twelve
+// products (no l.l; imma_kloop_reuse), certifies the arg-max with a Cauchy-Schwarz bound on the missing product and
+// settles the position by the peak-tuple look-up; frames it cannot certify get the l.l product from a second pass and
+// continue exactly as above, so every result stays bit-identical to the reference.
 #include <limits.h>
 #include <stdlib.h>
 
