@@ -473,3 +473,23 @@ def test_config4_batch_properties():
     torch.cuda.synchronize()
     assert torch.equal(rot["lags"], res["lags"][:n])
     loc.close()
+
+
+def test_certified_argmax_across_signal_levels(loc):
+    """The default tensor kernel certifies the arg-max from nine of the twelve digit products when its bound allows and
+    falls back to the exact path otherwise.  Sweep the signal level from barely above the noise to full scale so that
+    frames sit on both sides of the bound, and demand lags and cells identical to the integer-pipe kernel (which has
+    no shortcut and is itself oracle-checked) on every frame."""
+    torch = _torch()
+    F = 1 << 16
+    adc, _, _ = loc.synth_device(F, seed=99)
+    scale = (torch.arange(F, device="cuda") % 33).view(F, 1, 1).float() / 32.0          # 0 .. 1 in 33 steps
+    dimmed = (128.0 + (adc.float() - 128.0) * scale).round().clamp(0, 255).to(torch.uint8).contiguous()
+    got = loc.localize_device(dimmed, want=("lags", "cell", "stats"))
+    ref_loc = make_loc("imad")
+    exp = ref_loc.localize_device(dimmed, want=("lags", "cell"))
+    torch.cuda.synchronize()
+    assert torch.equal(got["lags"], exp["lags"]) and torch.equal(got["cell"], exp["cell"])
+    st = got["stats"].cpu().numpy()
+    assert 0 < st[4] < F, st          # both routes were taken
+    ref_loc.close()
