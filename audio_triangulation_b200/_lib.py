@@ -70,6 +70,8 @@ def load():
         "at_synchronize": (C.c_int, [ctx]),
         "at_average_device": (C.c_int, [ctx, vp, vp, vp, vp, vp, sz, u64, vp]),
         "at_heatmap_device": (C.c_int, [ctx, vp, sz, vp, vp, vp, vp, vp]),
+        "at_pair_max_shift": (C.c_int, [ctx, vp]),
+        "at_admissible_lags_device": (C.c_int, [ctx, vp, sz, vp, vp]),
         "at_synth_host": (C.c_int, [ctx, u64, C.c_uint32, sz, sz, vp, vp, vp]),
         "at_synth_device": (C.c_int, [ctx, u64, C.c_uint32, sz, sz, vp, vp, vp, vp]),
         "at_microbench": (C.c_int, [ctx, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

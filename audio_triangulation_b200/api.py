@@ -147,6 +147,22 @@ class Localizer:
                                            g("classes"), C.c_void_p(st.cuda_stream)))
         return res
 
+    def pair_max_shift(self):
+        """Physically admissible |lag| per pair: ceil(distance * sample rate / speed of sound), clipped to max_shift."""
+        out = np.zeros(self.n_pairs, np.int32)
+        L.check(self.lib.at_pair_max_shift(self.ctx, out.ctypes.data))
+        return out
+
+    def admissible_lags_device(self, curves, stream=None):
+        """First-max arg-max of int64 curves [F][pairs][2L+1] inside each pair's admissible window -> int32 [F][pairs]."""
+        import torch
+        assert curves.is_cuda and curves.dtype == torch.int64 and curves.is_contiguous()
+        F = curves.shape[0]
+        lags = torch.empty((F, self.n_pairs), dtype=torch.int32, device=curves.device)
+        st = stream if stream is not None else torch.cuda.current_stream(curves.device)
+        L.check(self.lib.at_admissible_lags_device(self.ctx, curves.data_ptr(), F, lags.data_ptr(), C.c_void_p(st.cuda_stream)))
+        return lags
+
     def gccphat_device(self, adc, heads=None, want_peak=False, stream=None):
         """FFT / GCC-PHAT variant of the TDOA stage (crossover study; not a reference algorithm)."""
         import torch

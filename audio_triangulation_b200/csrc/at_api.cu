@@ -76,6 +76,7 @@ struct at_context {
     float *d_mic_xy = nullptr; uint8_t *d_lut = nullptr; uint8_t *d_cand_idx = nullptr; int32_t *d_cand_cell = nullptr;
     uint8_t *d_cs_idx = nullptr; int32_t *d_cs_cell = nullptr; int32_t *d_cs_grid = nullptr; float2 *d_cell_xy = nullptr;
     int4 *d_peak_tab = nullptr;
+    int32_t *d_pair_lmax = nullptr; std::vector<int32_t> h_pair_lmax;   // admissible |lag| per pair
     int16_t *d_window = nullptr; float *d_gauss = nullptr; int32_t *d_delay_q8 = nullptr;
     // host copies
     std::vector<float> h_mic_xy; std::vector<uint8_t> h_lut; std::vector<int32_t> h_delay_q8;
@@ -125,7 +126,7 @@ extern "C" void at_destroy(at_context *c)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
-                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_peak_tab};
+                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_peak_tab, c->d_pair_lmax};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -171,6 +172,19 @@ static int create_impl(const at_config *cfg, at_context *c)
     CU(cudaMemcpyAsync(c->h_mic_xy.data(), c->d_mic_xy, sizeof(float) * 2 * M, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->h_lut.data(), c->d_lut, c->h_lut.size(), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+
+    // admissible lag window per pair: |lag| <= ceil(distance * fs / c), clipped to L (float32 as the geometry)
+    {
+        c->h_pair_lmax.clear();
+        for (int i = 0; i < M; i++)
+            for (int j = i + 1; j < M; j++) {
+                const float dx = c->h_mic_xy[2 * i] - c->h_mic_xy[2 * j], dy = c->h_mic_xy[2 * i + 1] - c->h_mic_xy[2 * j + 1];
+                const int lim = (int)ceilf(sqrtf(dx * dx + dy * dy) * cfg->sample_rate_hz / cfg->speed_of_sound);
+                c->h_pair_lmax.push_back(lim < L ? lim : L);
+            }
+        CU(cudaMalloc(&c->d_pair_lmax, sizeof(int32_t) * c->h_pair_lmax.size()));
+        CU(cudaMemcpy(c->d_pair_lmax, c->h_pair_lmax.data(), sizeof(int32_t) * c->h_pair_lmax.size(), cudaMemcpyHostToDevice));
+    }
 
     // distinct lag-index tuples, in order of first row-major appearance (index bookkeeping only)
     {
@@ -502,6 +516,22 @@ extern "C" int at_heatmap_device(at_context *c, const int64_t *d_corr, size_t n_
     CU(at_launch_heatmap((const long long *)d_corr, n_arrays, c->n_pairs, c->cfg.max_shift, c->d_lut, c->d_cand_idx,
                          c->d_cand_cell, c->n_cand, c->n_cells, c->cfg.half_w, c->cfg.half_h, c->cfg.px_per_m, d_cell,
                          (long long *)d_highest, d_xy, d_classes, (cudaStream_t)stream));
+    return AT_OK;
+}
+
+extern "C" int at_pair_max_shift(at_context *c, int32_t *out)
+{
+    if (!c || !out) return fail(AT_EINVAL, "at_pair_max_shift: null argument");
+    memcpy(out, c->h_pair_lmax.data(), sizeof(int32_t) * c->h_pair_lmax.size());
+    return AT_OK;
+}
+
+extern "C" int at_admissible_lags_device(at_context *c, const int64_t *d_curves, size_t n_frames, int32_t *d_lags, void *stream)
+{
+    if (!c || !d_curves || !d_lags) return fail(AT_EINVAL, "at_admissible_lags_device: null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(at_launch_admissible_lags((const long long *)d_curves, n_frames, c->n_pairs, c->cfg.max_shift, c->d_pair_lmax, d_lags,
+                                 (cudaStream_t)stream));
     return AT_OK;
 }
 

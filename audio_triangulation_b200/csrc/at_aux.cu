@@ -148,6 +148,24 @@ __global__ void average_kernel(long long *est, int32_t *est_best, unsigned long 
     if (lane == 0) { est_best[w] = b.i - L; est_time[w] = now_us; }                   // :62
 }
 
+// ------------------------------------------------------------------ arg-max inside each pair's admissible lag window
+// One warp per (frame, pair): first-max arg-max (correlations.c:20-23) over |s| <= lmax[pair].
+__global__ void admissible_lags_kernel(const long long *curves, size_t n_items, int n_pairs, int L, const int32_t *lmax,
+                                       int32_t *lags)
+{
+    const size_t item = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= n_items) return;
+    const int lane = threadIdx.x & 31, NL = 2 * L + 1, lp = lmax[item % n_pairs];
+    const long long *c = curves + item * NL;
+    Best b = {LLONG_MIN, 0x7fffffff};
+    for (int li = L - lp + lane; li <= L + lp; li += 32) {
+        const long long v = c[li];
+        if (v > b.v) { b.v = v; b.i = li; }
+    }
+    b = warp_best(b);
+    if (lane == 0) lags[item] = b.i - L;
+}
+
 // ------------------------------------------------------------------ stand-alone likelihood map
 // ref: components/vga/vga_heatmap.h:96-126 for arbitrary curves; one block per array.
 __global__ void heatmap_kernel(const long long *corr, int n_pairs, int L, const uint8_t *lut, const uint8_t *cand_idx,
@@ -482,6 +500,16 @@ cudaError_t at_launch_average(long long *d_est, int32_t *d_est_best, unsigned lo
     const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
     average_kernel<<<blocks, 256, 0, st>>>(d_est, d_est_best, d_est_time, d_fresh, d_gate, n_arrays, n_pairs, L,
                                            now_us, d_decay);
+    at_count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t at_launch_admissible_lags(const long long *d_curves, size_t n_frames, int n_pairs, int L, const int32_t *d_lmax,
+                                      int32_t *d_lags, cudaStream_t st)
+{
+    const size_t n_items = n_frames * (size_t)n_pairs;
+    if (!n_items) return cudaSuccess;
+    admissible_lags_kernel<<<(unsigned)((n_items + 7) / 8), 256, 0, st>>>(d_curves, n_items, n_pairs, L, d_lmax, d_lags);
     at_count_launch();
     return cudaGetLastError();
 }

@@ -82,6 +82,8 @@ cudaError_t at_launch_heatmap(const long long *d_corr, size_t n_arrays, int n_pa
                               int n_cand, int n_cells, int half_w, int half_h, float px_per_m,
                               int32_t *d_cell, long long *d_highest, float *d_xy, uint8_t *d_classes,
                               cudaStream_t st);
+cudaError_t at_launch_admissible_lags(const long long *d_curves, size_t n_frames, int n_pairs, int L, const int32_t *d_lmax,
+                                      int32_t *d_lags, cudaStream_t st);
 cudaError_t at_launch_synth(unsigned long long seed, unsigned flags, size_t first, size_t n_frames, int n_mics,
                             int n_bits, int n_cells, const int32_t *d_delay_q8, uint8_t *d_adc, int32_t *d_heads,
                             int32_t *d_cell, cudaStream_t st);

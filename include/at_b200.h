@@ -207,6 +207,17 @@ int at_average_device(at_context *ctx, int64_t *d_est, int32_t *d_est_best, uint
 int at_heatmap_device(at_context *ctx, const int64_t *d_corr /*[A][pairs][2L+1]*/, size_t n_arrays,
                       int32_t *d_cell, int64_t *d_highest, float *d_xy, uint8_t *d_classes, void *stream);
 
+/* Physically admissible lag window of each pair: a source cannot delay one microphone against the other by more than
+ * their distance, so |lag| <= ceil(d_pair * sample_rate / speed_of_sound), clipped to max_shift.  The reference scans
+ * +-max_shift for every pair (components/constants.h:12 derives it from the longest side); this is the per-pair
+ * refinement of SURVEY section 8(f) item 3, offered as a separate step so that the reference's results stay untouched.
+ * out: int32 [pairs] in pair order (0,1), (0,2), ..., (1,2), ... */
+int at_pair_max_shift(at_context *ctx, int32_t *out);
+/* First-max arg-max (components/correlations.c:20-23: strict '>', ascending lag) of raw or post-Gaussian curves
+ * restricted to each pair's admissible window.  d_curves: int64 [F][pairs][2L+1] (the `raw` or packed `corr` output of
+ * at_localize_device); d_lags: int32 [F][pairs].  Device pointers, asynchronous on `stream`. */
+int at_admissible_lags_device(at_context *ctx, const int64_t *d_curves, size_t n_frames, int32_t *d_lags, void *stream);
+
 /* GCC-PHAT / FFT variant of the TDOA stage (hand-written radix-2 FFT, no cuFFT), for the direct-vs-FFT crossover
  * study of long frames / wide lag ranges.  NOT a reference algorithm (the reference correlates directly,
  * components/correlations.c:9-24): PHAT whitening changes the statistic, only arg-max lags are comparable.

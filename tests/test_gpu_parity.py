@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from frames import burst_frames
+from frames import burst_frames, kat_frames
 from oracle_bindings import CELLS, CORR_DT, HALF_H, HALF_W, HEIGHT, PX_PER_M, RATE_HZ, SPEED, L, N, NL, Oracle
 
 pytestmark = pytest.mark.gpu
@@ -493,3 +493,28 @@ def test_certified_argmax_across_signal_levels(loc):
     st = got["stats"].cpu().numpy()
     assert 0 < st[4] < F, st          # both routes were taken
     ref_loc.close()
+
+
+def test_admissible_lag_windows(loc):
+    """Per-pair admissible lag windows (an extension -- the reference scans +-46 for every pair):
+    window = ceil(distance * fs / c), and the windowed first-max arg-max equals a numpy restatement on the raw curves."""
+    torch = _torch()
+    lim = loc.pair_max_shift()
+    mics = loc.mics().astype(np.float32)
+    exp_lim = []
+    for i in range(3):
+        for j in range(i + 1, 3):
+            d = np.float32(np.sqrt(np.float32((mics[i, 0] - mics[j, 0]) ** 2 + (mics[i, 1] - mics[j, 1]) ** 2)))
+            exp_lim.append(min(L, int(np.ceil(np.float32(d * np.float32(RATE_HZ)) / np.float32(SPEED)))))
+    assert lim.tolist() == exp_lim == [20, 30, 22]          # sides 0.132 / 0.20 / 0.15 m at 50 kHz, 343 m/s
+    names, kats = kat_frames()
+    bursts, _ = burst_frames(200, seed=12, max_delay=45)    # delays beyond the windows: the two arg-maxes must differ somewhere
+    adc = np.concatenate([kats, bursts])
+    r = loc.localize_device(torch.from_numpy(adc).cuda(), want=("lags", "raw"))
+    got = loc.admissible_lags_device(r["raw"]).cpu().numpy()
+    raw = r["raw"].cpu().numpy()
+    exp = np.stack([np.argmax(raw[:, p, L - lim[p]:L + lim[p] + 1], axis=1) - lim[p] for p in range(3)], axis=1)   # argmax = first max
+    assert (got == exp).all()
+    full = r["lags"].cpu().numpy()
+    inside = np.abs(full) <= lim[None, :]
+    assert (got[inside] == full[inside]).all() and (~inside).any()
