@@ -7,11 +7,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libat_b200.so")
+# AT_LIB_VARIANT=checked | prof selects a debug build of the same library (csrc/Makefile); default: the product
+_VARIANT = os.environ.get("AT_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "libat_b200%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 
 AT_OK, AT_EINVAL, AT_ECUDA, AT_ENOGPU, AT_ENOMEM = 0, -1, -2, -3, -4
 AT_MAX_MICS = 8
-KERNELS = {"auto": 0, "imad": 1, "imma": 2, "imma_lm": 3, "umma": 4}
+KERNELS = {"auto": 0, "imad": 1, "imma": 2, "umma": 4}
 AT_CORR_PACKED, AT_CORR_STRUCT = 0, 1
 SYNTH_INTEGER_DELAYS, SYNTH_RANDOM_HEADS, SYNTH_KATS = 1, 2, 4
 UBENCH = {"imad_wide": 0, "imad": 1, "dp2a": 2, "dp4a": 3, "imma_s8": 4, "lds": 5, "dfma": 6}

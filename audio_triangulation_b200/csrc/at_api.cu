@@ -84,6 +84,9 @@ struct at_context {
     HostSlot slot[2];
     void *d_scratch = nullptr; size_t scratch_bytes = 0;
     float2 *d_spec = nullptr; size_t spec_frames = 0;   // GCC-PHAT spectra scratch
+    // at_average_device: time stamps read back / per-entry decay factors computed on the host
+    uint64_t *h_avg_time = nullptr; float *h_avg_decay = nullptr; float *d_avg_decay = nullptr; size_t avg_cap = 0;
+    bool umma_window_ok = false;                        // at_fused_umma_window_ok(window)
 };
 
 static int ensure(void **p, size_t bytes)
@@ -128,6 +131,9 @@ extern "C" void at_destroy(at_context *c)
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
                     c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_peak_tab, c->d_pair_lmax};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->h_avg_time) cudaFreeHost(c->h_avg_time);
+    if (c->h_avg_decay) cudaFreeHost(c->h_avg_decay);
+    if (c->d_avg_decay) cudaFree(c->d_avg_decay);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -250,6 +256,14 @@ static int create_impl(const at_config *cfg, at_context *c)
         pick_window(cfg->n_bits, w);
         CU(cudaMalloc(&c->d_window, sizeof(int16_t) * w.size()));
         CU(cudaMemcpy(c->d_window, w.data(), sizeof(int16_t) * w.size(), cudaMemcpyHostToDevice));
+        c->umma_window_ok = at_fused_umma_window_ok(w.data(), (int)w.size());
+    }
+    {   // the tcgen05 kernel's redo list comes from the device's memory pool: keep freed blocks instead of returning them
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
     }
     // Gaussian factors exp(-d^2/36) for d = 0..2L with the host libm, exactly as
     // correlations.c:30 evaluates them (float division, double exp, rounded to float).
@@ -339,18 +353,46 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
     p.n_cand = c->n_cand; p.n_cells = c->n_cells; p.half_w = c->cfg.half_w; p.half_h = c->cfg.half_h;
     p.px_per_m = c->cfg.px_per_m;
     if (kernel == AT_KERNEL_AUTO) {   // the fastest measured kernel of each shape
+        static const char *auto3 = getenv("AT_AUTO_3MIC");   // "imma": keep the mma.sync kernel for the reference shape
         if (sh.n_mics == 8 && sh.n_bits == 12 && at_fused_umma_m_supports(sh) && !p.sig16) kernel = AT_KERNEL_UMMA;   // 2.8x the mma.sync form
+        else if (at_fused_umma_supports(sh) && c->umma_window_ok && !p.sig16 && !(auto3 && !strcmp(auto3, "imma"))) kernel = AT_KERNEL_UMMA;
         else kernel = (at_fused_imma_supports(sh) || at_fused_imma_cta_supports(sh)) ? AT_KERNEL_IMMA : AT_KERNEL_IMAD;
     }
     cudaError_t e;
     if (kernel == AT_KERNEL_UMMA) {
         if (p.sig16) return fail(AT_EINVAL, "UMMA kernels take ADC bytes, not prepared int16 frames");
-        if (at_fused_umma_supports(sh)) e = at_launch_fused_umma(sh, p, c->sm_count, st);             // 3 mics x 1024
-        else if (at_fused_umma_m_supports(sh)) e = at_launch_fused_umma_m(sh, p, c->sm_count, st);    // 8 mics x 1024 / 4096
+        if (at_fused_umma_supports(sh)) {                                                             // 3 mics x 1024
+            if (!c->umma_window_ok) return fail(AT_EINVAL, "UMMA kernel: packed accumulators could overflow with this window");
+            // scratch for the frames the certified pass hands to the exact pass (stream-ordered, from the device's pool)
+            uint32_t *redo = nullptr;
+            const bool curves = p.raw || p.corr || p.classes || p.highest;
+            if (!curves && p.n_frames < (1ull << 32)) {
+                CU(cudaMallocAsync((void **)&redo, 4 * (size_t)(p.n_frames + 1), st));
+                CU(cudaMemsetAsync(redo, 0, 4, st));
+            }
+#ifdef AT_PROF
+            static unsigned long long *d_prof = nullptr;
+            if (!d_prof) CU(cudaMalloc((void **)&d_prof, 32 * 8));
+            CU(cudaMemsetAsync(d_prof, 0, 32 * 8, st));
+            p.prof = d_prof;
+#endif
+            e = at_launch_fused_umma(sh, p, redo, c->sm_count, st);
+            if (redo) CU(cudaFreeAsync(redo, st));
+#ifdef AT_PROF
+            if (e == cudaSuccess && getenv("AT_PROF_PRINT")) {
+                unsigned long long h[32];
+                CU(cudaStreamSynchronize(st));
+                CU(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
+                static const char *role[4] = {"mma-issue", "prep", "epi-q0", "epi-q1-3"};
+                for (int r = 0; r < 4; r++) {
+                    fprintf(stderr, "AT_PROF %-9s cycles/frame/SM (summed over the role's warps):", role[r]);
+                    for (int k = 0; k < 8; k++) fprintf(stderr, " %8.1f", (double)h[r * 8 + k] / ((double)p.n_frames / c->sm_count));
+                    fprintf(stderr, "\n");
+                }
+            }
+#endif
+        } else if (at_fused_umma_m_supports(sh)) e = at_launch_fused_umma_m(sh, p, c->sm_count, st);    // 8 mics x 1024 / 4096
         else return fail(AT_EINVAL, "UMMA kernel has no instantiation for this shape");
-    } else if (kernel == AT_KERNEL_IMMA_LM) {
-        if (!at_fused_imma3_supports(sh)) return fail(AT_EINVAL, "IMMA-LM kernel has no instantiation for this shape");
-        e = at_launch_fused_imma3(sh, p, c->sm_count, st);
     } else if (kernel == AT_KERNEL_IMMA) {
         if (at_fused_imma_supports(sh)) e = at_launch_fused_imma(sh, p, c->sm_count, st);             // warp per frame, 3 mics
         else if (at_fused_imma_cta_supports(sh)) e = at_launch_fused_imma_cta(sh, p, c->sm_count, st); // CTA per frame, M mics
@@ -501,10 +543,39 @@ extern "C" int at_average_device(at_context *c, int64_t *d_est, int32_t *d_est_b
                                  void *stream)
 {
     if (!c || !d_est || !d_est_best || !d_est_time || !d_fresh) return fail(AT_EINVAL, "at_average_device: null argument");
+    if (!n_arrays) return AT_OK;
     CU(cudaSetDevice(c->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // decay = 1 - exp(-dt / 0.5) is evaluated on the HOST with the same libm call as correlations.c:42-43, one value per
+    // (array, pair), so that the float is the reference's bit for bit (the CUDA exp() is within an ulp, not identical).
+    // Costs one small read-back of the time stamps; arrays updated together share their dt, so exp() runs once per
+    // distinct dt.
+    const size_t n = n_arrays * (size_t)c->n_pairs;
+    if (c->avg_cap < n) {
+        if (c->h_avg_time) { cudaFreeHost(c->h_avg_time); c->h_avg_time = nullptr; }
+        if (c->h_avg_decay) { cudaFreeHost(c->h_avg_decay); c->h_avg_decay = nullptr; }
+        if (c->d_avg_decay) { CU(cudaDeviceSynchronize()); cudaFree(c->d_avg_decay); c->d_avg_decay = nullptr; }
+        CU(cudaMallocHost((void **)&c->h_avg_time, n * 8));
+        CU(cudaMallocHost((void **)&c->h_avg_decay, n * 4));
+        CU(cudaMalloc((void **)&c->d_avg_decay, n * 4));
+        c->avg_cap = n;
+    }
+    CU(cudaMemcpyAsync(c->h_avg_time, d_est_time, n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    uint64_t last_t = ~0ull;
+    float last_decay = 0.f;
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t t = c->h_avg_time[i];
+        if (t != last_t || i == 0) {
+            const float dt = (float)(now_us - t) / 1e6f;                     // correlations.c:42
+            last_decay = (float)(1.0 - exp((double)(-dt / 0.5f)));           // correlations.c:43 (1.f - double -> double, stored as float)
+            last_t = t;
+        }
+        c->h_avg_decay[i] = last_decay;
+    }
+    CU(cudaMemcpyAsync(c->d_avg_decay, c->h_avg_decay, n * 4, cudaMemcpyHostToDevice, st));
     CU(at_launch_average((long long *)d_est, d_est_best, (unsigned long long *)d_est_time, (const long long *)d_fresh,
-                         d_gate, n_arrays, c->n_pairs, c->cfg.max_shift, now_us, nullptr,
-                         (cudaStream_t)stream));
+                         d_gate, n_arrays, c->n_pairs, c->cfg.max_shift, now_us, c->d_avg_decay, st));
     return AT_OK;
 }
 

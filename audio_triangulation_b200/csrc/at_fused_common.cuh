@@ -11,9 +11,19 @@
 //   components/vga/vga_heatmap.h:96-108 L(cell) = sum_pairs c[lut], max, (ours) first cell
 //   sample_compute.h:124-134            gate = sum best^2 > 4
 #pragma once
+#include <stdio.h>
+
 #include "at_internal.h"
 
 namespace atk {
+
+// Debug build (make CHECKED=1 -> -DAT_CHECKED): index / ownership assertions inside the kernels; a failed one prints
+// its location and traps, so the launch returns an error instead of silently corrupting shared memory or TMEM.
+#ifdef AT_CHECKED
+#define AT_CHECK(cond) do { if (!(cond)) { printf("AT_CHECK failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define AT_CHECK(cond) do { } while (0)
+#endif
 
 constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 constexpr int round_up(int a, int b) { return ceil_div(a, b) * b; }

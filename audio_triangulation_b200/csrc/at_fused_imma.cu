@@ -163,12 +163,6 @@ __device__ __forceinline__ void imma_kloop_reuse(int (&acc)[3][3][4], uint32_t y
             for (int c = 0; c < 4; c++) acc[a][b][c] += accS[a][b][c ^ 2];
 }
 
-// sqrt(a * b) rounded up (a, b < 2^27): float product and approximate root, both within 2^-20, times 1 + 2^-16
-__device__ __forceinline__ float sqrt_prod_up(unsigned a, unsigned b)
-{
-    return sqrtf((float)a * (float)b) * 1.0000153f + 1.0f;
-}
-
 template <int NBITS, int L, int WARPS, int CTAS_PER_SM, int UNROLL, bool PRUNE>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(const AtFusedParams p)
 {

@@ -1,4 +1,5 @@
-// at_fused_umma.cu -- fused localization kernel on the 5th-generation tensor cores (tcgen05 / UMMA), AT_KERNEL_UMMA.
+// at_fused_umma.cu -- fused localization kernel of the reference shape (3 microphones x 1024 samples) on the
+// 5th-generation tensor cores (tcgen05 / UMMA, accumulators in TMEM): AT_KERNEL_UMMA, the default for this shape.
 //
 // Polyphase form of the lagged cross-correlation (ref: components/correlations.c:9-18,
 //     corr[s] = sum_i x[i] * y[i+s]).  Split time as i = 16 q + phi.  With Y the zero-padded y frame
@@ -9,205 +10,313 @@
 //     A[m][q] = Y[m + 16 q]  is a Hankel matrix -- MN chunks 16 bytes apart (SBO = 16 B), K rows 16 bytes apart, so
 //                            the chunks overlap in memory and nothing is materialised;
 //     B[n][q] = x[n + 16 q]  is the polyphase matrix of x; several planes sit side by side (SBO = plane stride).
-// One tcgen05.mma kind::i8 (K = 32) covers 512 samples, so a frame needs 2 K-steps instead of 33 mma.sync steps.
-// (tools/probes/umma_probe.cu is the stand-alone proof of this operand trick.)
+// One tcgen05.mma kind::i8 (K = 32) covers 512 samples: 2 K-steps per frame instead of 33 mma.sync steps.
 //
-// int16 samples are split into balanced signed digits w = 256 h + l, h and l both in [-128, 127] (possible because
-// the windowed samples stay inside [-32767, 32511]); corr = 65536 (h.h) + 256 (h.l + l.h) + (l.l) as in the
-// mma.sync kernel, each of the four digit products in its own 16 TMEM columns, int32 (|sum| < 2^26), recombined in
-// int64: bit-exact.  An MMA of this shape costs about (A bytes + B bytes) / 128 cycles whatever N is (measured,
-// tools/probes/umma_probe.cu: 46 cycles at N = 16..64), so the x planes are batched into one wide B operand.
+// int16 samples are split into balanced signed digits w = 256 h + l, h and l both in [-128, 127];
+//     corr = 65536 (h.h) + 256 (h.l + l.h) + (l.l).
+// Tiles of 16 TMEM columns per pair: hh, mid = hl + lh (two MMAs accumulate into the same columns) and, in the exact
+// variant, ll; int32 (|sum| < 2^26).  With H(p) the Hankel view of plane p, per K-step
+//     H(c.h) x [a.h b.h a.l b.l] -> [hh_ac hh_bc mid_ac mid_bc]        H(b.h) x [a.h a.l] -> [hh_ab mid_ab]
+//     H(c.l) x [a.h b.h]        +-> [mid_ac mid_bc]                     H(b.l) x [a.h]    +-> [mid_ab]
+// = 8 MMAs per frame (419 cycles per frame and SM, tools/probes/epi_probe.cu); the exact variant adds
+//     H(c.l) x [a.l b.l] -> [ll_ac ll_bc]   H(b.l) x [a.l] -> [ll_ab]    (10 MMAs, 507 cycles).
 //
-// The diagonal sums are the CUDA cores' job.  To halve them every plane is stored twice, the second copy advanced by
-// 8 bytes, and both copies are accumulated into the same tile:  D2[m][phi] = D[m][phi] + D[m+8][phi+8]  for
-// phi = 0..7, i.e. two entries of the same diagonal; corr[s] = sum_{phi<8} D2[s + PAD + phi][phi].
+// The diagonal sums are the CUDA cores' job and never touch shared memory: an epilogue warp reads its 32 TMEM lanes
+// (tcgen05.ld 32x32b: lane = row m, 16 registers = the phases), packs U = 256 hh + mid (|U| < 2^31 for this window,
+// checked at context creation) and runs a five-stage register butterfly (diag_butterfly, at_umma_common.cuh): after
+// stage k a lane holds the lags congruent to it modulo 2^(k+1); 16 shuffles per tile.  Only the 15 partial sums that
+// cross a 32-row quarter go through shared memory.
 //
-// CTA = 16 warps, one CTA per SM, persistent, warp-specialised:
-//   warp 0      one lane issues, frame after frame, the 16 MMAs of a frame (2 K-steps x 2 copies x 4 y planes; the
-//               B operand is the four x planes a.h a.l b.h b.l side by side, N = 64) and commits them to two mbarriers
-//               (accumulators ready / planes free);
-//   warps 1-7   prep: one frame each -- coalesced 16-byte loads, DC removal, <<8, window (as imma_prep16), digit
-//               planes to shared memory (both copies), mbarrier arrive;
-//   warps 8-15  two epilogue sets of four warps, set k bound to TMEM slot k (192 columns = 12 tiles): TMEM ->
-//               registers (warp w reads lane quadrant w % 4), transposing scatter through shared memory, diagonal
-//               sums, int64 recombination, first-max arg-max (correlations.c:20-23), then peak-tuple look-up or the
-//               warp-scope epilogue of at_imma_common.cuh for everything else.
+// Two instantiations.
+//   CERT  (lags / cell / xy / gate): only C9 = 256 U is computed.  The missing l.l product obeys
+//         |ll[s]| <= sqrt(Sl_x Sl_y) =: B (Cauchy-Schwarz; the sums of squared low digits come from the frame
+//         preparation), so if the maximum of U exceeds every other lag by more than 2 B / 256 its lag is THE arg-max of
+//         the exact curve (no tie possible) and the position follows from the peak-tuple table.  Frames that cannot
+//         be settled this way are appended to a list in global memory.
+//   EXACT (whole curves, and the frames on that list): all twelve products, int64 curves, the exact epilogue.
+// at_launch_fused_umma launches CERT followed by EXACT on the list (its length is read on the device), so every
+// result is bit-identical to the reference either way.
 //
-// Status (measured on the B200): bit-exact on every parity test, 152 M frames/s -- 0.71x the mma.sync
-// kernel, which therefore stays the default.  Two things bound it: an MMA of this shape costs ~63-73 cycles whatever
-// N <= 64 is (4 KB of A operand per instruction, fetched at ~64-128 B/clk: 16 MMAs = ~1 170 cycles per frame), and the
-// 9 x 8 x 128 diagonal terms per frame have to be added by the CUDA cores.
+// CTA = 28 warps, one CTA per SM, persistent, warp-specialised.  The warp scheduler prefers the highest warp id of a
+// sub-partition, so the roles are numbered by how little they may be delayed:
+//   warp 27      one elected lane issues the MMAs of a frame and commits them to two mbarriers
+//                (accumulators ready / planes free);
+//   warps 20-26  frame preparation, one frame each, two staging and two plane buffers per warp: the raw frame arrives
+//                by a 1-D bulk copy (TMA) one frame ahead; DC removal, <<8, window (held in registers: lane l always
+//                prepares samples [16 l, 16 l + 16) of both frame halves; any ring head: unaligned heads are realigned
+//                in registers), digit planes to shared memory;
+//   warps 0-19   five epilogue sets of four warps; TMEM holds five accumulator slots (three in the exact variant).
 #include <limits.h>
 #include <stdlib.h>
 
 #include "at_imma_common.cuh"
 #include "at_umma_common.cuh"
 
+// make VARIANT=prof: every warp accumulates the cycles it spends in each section of its role (lane 0, clock64) and adds
+// them to p.prof[role * 8 + section] when it leaves the kernel; tools/umma_prof.py prints them per frame.
+#ifdef AT_PROF
+#define PROF_DECL unsigned long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_MARK(k) do { const unsigned long long t_ = clock64(); prof_acc[k] += t_ - prof_t; prof_t = t_; } while (0)
+#define PROF_FLUSH(role) do { if (lane == 0 && p.prof) for (int k_ = 0; k_ < 8; k_++) atomicAdd(&p.prof[(role) * 8 + k_], prof_acc[k_]); } while (0)
+#else
+#define PROF_DECL do { } while (0)
+#define PROF_MARK(k) do { } while (0)
+#define PROF_FLUSH(role) do { } while (0)
+#endif
+
 namespace atk {
 
-template <int L>
+template <int L, bool CERT>
 struct UmmaGeo {
     static constexpr int N = 1024, NBITS = 10;
     static constexpr int PAD = 48;                      // lag index j = s + PAD; also the left zero pad of a plane
     static constexpr int PLANE = 1152;                  // bytes per plane buffer: 48 zeros, 1024 samples, 80 zeros
-    static constexpr int NPLANES = 12;                  // [copy][channel a,b,c][h,l]; copy 1 = copy 0 advanced by 8 bytes
-    static constexpr int FRAME = NPLANES * PLANE;       // 13 824 bytes of planes per frame
+    static constexpr int NPLANES = 6;                   // a.h b.h a.l b.l c.h c.l
+    static constexpr int FRAME = NPLANES * PLANE;       // 6 912 bytes of planes per frame
     static constexpr int NJ = 96;                       // lag slots kept (j = 0..95), j in [PAD-L, PAD+L] are real
     static constexpr int NL = 2 * L + 1;
-    static constexpr int ZP = 136;                      // words per (pair, class, phase) column of the transposing scratch
-    static constexpr int TCOLS = 192;                   // TMEM columns per frame: 12 tiles (3 pairs x {hh, hl, lh, ll}) x 16
-    static constexpr int PREP_WARPS = 7, SETS = 2;      // warp 0 issues the MMAs, warps 1-7 prepare, warps 8-15 = 2 epilogue sets
+    static constexpr int TCOLS = CERT ? 96 : 160;       // TMEM columns per accumulator slot (96 / 144 used)
+    static constexpr int SLOTS = CERT ? 5 : 3;
+    static constexpr int PREP_WARPS = 7, PBUF = 2, SETS = 5, META = 32;
+    static constexpr int THREADS = 32 * (1 + PREP_WARPS + 4 * SETS);
     static_assert(PAD >= L && PAD + L + 15 < 128 && PAD + L < NJ, "lag window must fit the 128-row tile");
-    static_assert(127 + 16 * 63 + 8 < PLANE, "A operand reads stay inside a plane buffer");
+    static_assert(127 + 16 * 63 + 16 <= PLANE, "A operand reads stay inside a plane buffer");
+    static_assert(SLOTS * TCOLS <= 512, "TMEM columns");
+    static constexpr int PREP0 = 4 * SETS, MMAW = PREP0 + PREP_WARPS;   // first prep warp, MMA warp (epilogue warp w owns TMEM lane quarter w % 4)
+    static_assert(META >= PREP_WARPS * PBUF + SLOTS + SETS, "meta ring must outlive every frame in flight");
+    // first TMEM column (within a slot) of the hh (0) / mid (1) / ll (2) tile of pair 0 = (a,b), 1 = (a,c), 2 = (b,c)
+    __host__ __device__ static constexpr int col(int pr, int cls)
+    {
+        return CERT ? (pr == 0 ? 64 + 16 * cls : 32 * cls + (pr == 2 ? 16 : 0))
+                    : (pr == 0 ? 96 + 16 * cls : 32 * cls + (pr == 2 ? 16 : 0));
+    }
 };
+// plane index of (channel, digit): the x-side operand lists [a.h b.h a.l b.l] and [a.h a.l] must be equally spaced
+__host__ __device__ constexpr int umma_plane(int ch, int digit) { return ch == 2 ? 4 + digit : ch + 2 * digit; }
 
-template <int L>
+template <int L, bool CERT>
 struct UmmaSmem {
-    using G = UmmaGeo<L>;
-    alignas(128) uint8_t planes[G::PREP_WARPS][G::FRAME];
-    alignas(16) int z[G::SETS][3][3][8][G::ZP];         // [set][pair][class][phase][row - phase + 7]
-    alignas(16) long long curve[G::SETS][3][G::NJ];     // raw curves by lag index (input of epilogue_warp)
-    alignas(16) long long part[G::SETS][3][4];          // per-block arg-max keys
-    alignas(16) uint32_t win2[G::N];
+    using G = UmmaGeo<L, CERT>;
+    alignas(128) uint8_t planes[G::PREP_WARPS * G::PBUF][G::FRAME];
+    alignas(128) uint8_t rawb[G::PREP_WARPS * G::PBUF][3 * G::N];   // ring-ordered ADC bytes, staged by bulk copies (TMA)
+    alignas(16) long long curve[CERT ? 1 : G::SETS][3][G::NJ];   // exact raw curves by lag index (input of epilogue_warp)
+    alignas(16) long long part64[G::SETS][3][4];        // exact variant: per-warp arg-max keys
+    alignas(16) int4 part[G::SETS][2][3][4];            // CERT: per-warp {max, arg-max, runner-up}
+    alignas(16) int spill[G::SETS][2][6][3][32];        // partial sums that cross a lane quarter: [array][quarter below][lane]
+    alignas(16) uint32_t meta[G::META][4];              // per frame: sum of squared low digits of each channel
     float gauss[2 * L + 1];
-    alignas(8) uint64_t full[G::SETS], empty[G::SETS], ready[G::PREP_WARPS], sfree[G::PREP_WARPS];
+    alignas(8) uint64_t full[G::SETS], empty[G::SLOTS], ready[G::PREP_WARPS * G::PBUF], sfree[G::PREP_WARPS * G::PBUF],
+        rawfull[G::PREP_WARPS * G::PBUF];
     uint32_t tmem_base;
 };
 
-template <int L>
-__global__ void __launch_bounds__(512, 1) at_fused_umma_kernel(const AtFusedParams p)
+// 16 bytes starting sh bytes (1..15) into the 32-byte pair (a, b)
+__device__ __forceinline__ uint4 realign16(const uint4 a, const uint4 b, int sh)
 {
-    using G = UmmaGeo<L>;
-    using S = UmmaSmem<L>;
+    const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int ws = sh >> 2, bs = (sh & 3) * 8;
+    uint32_t t[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) t[k] = ws == 0 ? c[k] : (ws == 1 ? c[k + 1] : (ws == 2 ? c[k + 2] : c[k + 3]));
+    return make_uint4(__funnelshift_r(t[0], t[1], bs), __funnelshift_r(t[1], t[2], bs), __funnelshift_r(t[2], t[3], bs),
+                      __funnelshift_r(t[3], t[4], bs));
+}
+
+// 16 ring-ordered ADC bytes of chronological samples [i0, i0 + 16) of one channel (staged in shared memory), any head
+__device__ __forceinline__ uint4 load_chrono16(const uint8_t *chan, int i0, int head)
+{
+    constexpr int N = 1024;
+    const int r = (i0 + head) & (N - 1), r0 = r & ~15, sh = r & 15;
+    uint4 x = *reinterpret_cast<const uint4 *>(chan + r0);
+    if (sh) x = realign16(x, *reinterpret_cast<const uint4 *>(chan + ((r0 + 16) & (N - 1))), sh);   // warp-uniform
+    return x;
+}
+
+template <int L, bool CERT>
+__global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_kernel(const AtFusedParams p)
+{
+    using G = UmmaGeo<L, CERT>;
+    using S = UmmaSmem<L, CERT>;
     constexpr int N = G::N, PAD = G::PAD, PLANE = G::PLANE, P = G::PREP_WARPS;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     S &s = *reinterpret_cast<S *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- one-time CTA set-up: zero the planes (pads stay zero), window, Gaussian factors, barriers, TMEM
-    for (int i = tid; i < (int)(sizeof(s.planes) / 16); i += 512)
+    // ---- one-time CTA set-up: zero the planes (pads stay zero), Gaussian factors, barriers, TMEM
+    for (int i = tid; i < (int)(sizeof(s.planes) / 16); i += G::THREADS)
         reinterpret_cast<uint4 *>(&s.planes[0][0])[i] = make_uint4(0, 0, 0, 0);
-    imma_win_fill(s.win2, p.window, N, tid, 512);
-    for (int i = tid; i < 2 * L + 1; i += 512) s.gauss[i] = p.gauss[i];
+    for (int i = tid; i < 2 * L + 1; i += G::THREADS) s.gauss[i] = p.gauss[i];
     if (tid == 0) {
-        for (int k = 0; k < G::SETS; k++) { mbar_init(&s.full[k], 1); mbar_init(&s.empty[k], 4); }
-        for (int w = 0; w < P; w++) { mbar_init(&s.ready[w], 1); mbar_init(&s.sfree[w], 1); }
+        for (int k = 0; k < G::SETS; k++) mbar_init(&s.full[k], 1);
+        for (int k = 0; k < G::SLOTS; k++) mbar_init(&s.empty[k], 4);
+        for (int w = 0; w < P * G::PBUF; w++) { mbar_init(&s.ready[w], 1); mbar_init(&s.sfree[w], 1); mbar_init(&s.rawfull[w], 1); }
         fence_barrier_init();
     }
-    if (warp == 0) {
+    if (warp == G::MMAW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s.tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
-    const unsigned long long nf = p.n_frames, gstride = gridDim.x;
-    // frames of this CTA: f = blockIdx.x + gridDim.x * i, i = 0, 1, 2, ...; frame i is prepared by prep warp i % P,
-    // accumulated in TMEM slot i % SETS and finished by epilogue set i % SETS.  Every mbarrier is waited on in phase
-    // order by exactly one party (a parity wait only distinguishes the current from the preceding phase).
+    // Work list: frames 0 .. n_frames-1, or the frames named by frame_list (its length is read here, on the device).
+    const unsigned long long nf = p.frame_list ? (unsigned long long)*p.list_count : p.n_frames, gstride = gridDim.x;
+    auto frame_of = [&](unsigned long long k) -> unsigned long long { return p.frame_list ? (unsigned long long)p.frame_list[k] : k; };
+    // Frames of this CTA: k = blockIdx.x + gridDim.x * i, i = 0 .. mine-1; frame i is prepared by prep warp i % P into
+    // its buffers (i / P) % 2, accumulated in TMEM slot i % SLOTS and finished by epilogue set i % SETS.  Every
+    // mbarrier is waited on in phase order by exactly one party (a parity wait only distinguishes the current from the
+    // preceding phase): ready / sfree / rawfull per plane buffer, full per epilogue set, empty per TMEM slot.
+    const unsigned mine = nf > blockIdx.x ? (unsigned)((nf - blockIdx.x + gstride - 1) / gstride) : 0u;
 
-    if (warp == 0) {
+    if (warp == G::MMAW) {
         // =================================================================== MMA issue (one elected lane, frames in order)
-        constexpr uint32_t I64 = umma_idesc(64), I32 = umma_idesc(32);
-        constexpr uint32_t LBO = (128u >> 4) << 16;                     // K groups of 8 rows are 128 bytes apart
-        constexpr uint32_t HI_A = (16u >> 4) | 0x4000u;                 // A: MN chunks 16 bytes apart (Hankel), version 1
-        constexpr uint32_t HI_B = ((uint32_t)PLANE >> 4) | 0x4000u;     // B: one 16-phase chunk per x plane
-        for (unsigned long long i = 0;; i++) {
-            if (blockIdx.x + gstride * i >= nf) break;
-            const unsigned w = (unsigned)(i % P), v = (unsigned)(i / P), slot = (unsigned)(i % G::SETS), u = (unsigned)(i / G::SETS);
-            mbar_wait(&s.ready[w], v & 1);                          // planes of frame i are in shared memory
-            if (u >= 1) mbar_wait(&s.empty[slot], (u - 1) & 1);     // the epilogue set has drained the slot
+        constexpr uint32_t I64 = umma_idesc(64), I32 = umma_idesc(32), I16 = umma_idesc(16);
+        constexpr uint32_t LBO = (128u >> 4) << 16;                          // K groups of 8 rows are 128 bytes apart
+        constexpr uint32_t HI_A = (16u >> 4) | 0x4000u;                      // A: MN chunks 16 bytes apart (Hankel), version 1
+        constexpr uint32_t HI_B1 = ((uint32_t)PLANE >> 4) | 0x4000u;         // B: 16 phases per plane, consecutive planes
+        constexpr uint32_t HI_B2 = ((uint32_t)(2 * PLANE) >> 4) | 0x4000u;   // B: every other plane ([a.h a.l])
+        static_assert(umma_plane(0, 0) == 0 && umma_plane(1, 0) == 1 && umma_plane(0, 1) == 2 && umma_plane(1, 1) == 3, "x-side operand order");
+        constexpr int CH = umma_plane(2, 0), CL = umma_plane(2, 1), BH = umma_plane(1, 0), BL = umma_plane(1, 1), AL = umma_plane(0, 1);
+        PROF_DECL;
+        // i % P, i / P, i % SLOTS, i / SLOTS, i % SETS kept incrementally
+        unsigned pw = 0, v = 0, slot = 0, u = 0, eset = 0;
+        for (unsigned i = 0; i < mine; i++) {
+            const unsigned pb = pw * G::PBUF + (v & 1), pv = v >> 1;
+            PROF_MARK(0);
+            mbar_wait(&s.ready[pb], pv & 1);                        // planes of frame i are in shared memory
+            PROF_MARK(1);
+            if (u >= 1) mbar_wait(&s.empty[slot], (u - 1) & 1);     // the epilogue has drained the slot
+            PROF_MARK(2);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t b16 = (smem_u32(&s.planes[w][0]) >> 4) + LBO;   // start-address field of plane a.h, copy 0
+                const uint32_t b16 = (smem_u32(&s.planes[pb][0]) >> 4) + LBO;
                 const uint32_t cb = tmem + slot * G::TCOLS;
-                if (!(p.debug_skip & 2))
+                auto hk = [&](int pl, int kk) { return b16 + (uint32_t)((pl * PLANE + 512 * kk) >> 4); };          // Hankel view of a plane
+                auto xs = [&](int pl, int kk) { return b16 + (uint32_t)((pl * PLANE + PAD + 512 * kk) >> 4); };    // polyphase view, first plane pl
+                if (!(p.debug_skip & 2)) {
+                    if constexpr (CERT) {
 #pragma unroll
-                for (int kk = 0; kk < 2; kk++)
-#pragma unroll
-                    for (int copy = 0; copy < 2; copy++) {
-                        const uint32_t acc = (kk | copy) ? 1u : 0u;
-                        const uint32_t pl = b16 + (uint32_t)((copy * 6 * PLANE + 512 * kk) >> 4);   // plane a.h of this copy, K step kk
-                        const uint32_t xb = pl + (PAD >> 4);            // B: x planes a.h a.l b.h b.l side by side
-                        // A: one y plane, 128 Hankel rows.  Tiles: [x.h | x.l] per x channel.
-                        umma_i8_lohi(cb + 0, pl + 4 * (PLANE >> 4), HI_A, xb, HI_B, I64, acc);     // c.h: ac hh, ac hl, bc hh, bc hl
-                        umma_i8_lohi(cb + 64, pl + 5 * (PLANE >> 4), HI_A, xb, HI_B, I64, acc);    // c.l: ac lh, ac ll, bc lh, bc ll
-                        umma_i8_lohi(cb + 128, pl + 2 * (PLANE >> 4), HI_A, xb, HI_B, I32, acc);   // b.h: ab hh, ab hl
-                        umma_i8_lohi(cb + 160, pl + 3 * (PLANE >> 4), HI_A, xb, HI_B, I32, acc);   // b.l: ab lh, ab ll
+                        for (int kk = 0; kk < 2; kk++) {
+                            umma_i8_lohi(cb + G::col(1, 0), hk(CH, kk), HI_A, xs(0, kk), HI_B1, I64, kk);
+                            umma_i8_lohi(cb + G::col(1, 1), hk(CL, kk), HI_A, xs(0, kk), HI_B1, I32, 1);
+                            umma_i8_lohi(cb + G::col(0, 0), hk(BH, kk), HI_A, xs(0, kk), HI_B2, I32, kk);
+                            umma_i8_lohi(cb + G::col(0, 1), hk(BL, kk), HI_A, xs(0, kk), HI_B2, I16, 1);
+                        }
+                    } else {
+                        umma_i8_lohi(cb + G::col(1, 0), hk(CH, 0), HI_A, xs(0, 0), HI_B1, I64, 0);
+                        umma_i8_lohi(cb + G::col(1, 1), hk(CL, 0), HI_A, xs(0, 0), HI_B1, I32, 1);
+                        umma_i8_lohi(cb + G::col(1, 2), hk(CL, 0), HI_A, xs(AL, 0), HI_B1, I32, 0);
+                        umma_i8_lohi(cb + G::col(0, 0), hk(BH, 0), HI_A, xs(0, 0), HI_B2, I32, 0);
+                        umma_i8_lohi(cb + G::col(0, 1), hk(BL, 0), HI_A, xs(0, 0), HI_B2, I16, 1);
+                        umma_i8_lohi(cb + G::col(0, 2), hk(BL, 0), HI_A, xs(AL, 0), HI_B2, I16, 0);
+                        umma_i8_lohi(cb + G::col(1, 0), hk(CH, 1), HI_A, xs(0, 1), HI_B1, I64, 1);
+                        umma_i8_lohi(cb + G::col(1, 1), hk(CL, 1), HI_A, xs(0, 1), HI_B1, I64, 1);
+                        umma_i8_lohi(cb + G::col(0, 0), hk(BH, 1), HI_A, xs(0, 1), HI_B2, I32, 1);
+                        umma_i8_lohi(cb + G::col(0, 1), hk(BL, 1), HI_A, xs(0, 1), HI_B2, I32, 1);
                     }
-                umma_commit(&s.full[slot]);
-                umma_commit(&s.sfree[w]);
+                }
+                umma_commit(&s.full[eset]);
+                umma_commit(&s.sfree[pb]);
             }
             __syncwarp();
+            if (++pw == P) { pw = 0; v++; }
+            if (++slot == G::SLOTS) { slot = 0; u++; }
+            if (++eset == G::SETS) eset = 0;
+            PROF_MARK(3);
         }
-    } else if (warp <= P) {
+        PROF_FLUSH(0);
+    } else if (warp >= G::PREP0) {
         // =================================================================== prep warps
-        const int w = warp - 1;
-        uint8_t *const buf = &s.planes[w][0];
-        auto plane = [&](int copy, int ch, int hl) -> uint8_t * { return buf + ((copy * 3 + ch) * 2 + hl) * PLANE; };
-        for (unsigned long long i = w;; i += P) {
-            const unsigned long long f = blockIdx.x + gstride * i;
-            if (f >= nf) break;
-            const unsigned v = (unsigned)(i / P);
-            const uint8_t *src = p.adc + f * (unsigned long long)(3 * N);
+        const int w = warp - G::PREP0;
+        // Lane l owns the chronological samples [512 q + 16 l, +16) of every channel and frame: its slice of the doubled
+        // window, pre-masked for IDP.2A (even samples in the low half, odd samples in the high half), lives in registers.
+        uint32_t wr[2][16];
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int e = 0; e < 16; e++) wr[q][e] = (uint32_t)(2 * (int)p.window[q * 512 + lane * 16 + e]) << ((e & 1) * 16);
+        PROF_DECL;
+        // Raw frames arrive by 1-D bulk copies (TMA) into this warp's two staging buffers, one frame ahead: lane 0 starts
+        // the copy of frame i + P as soon as the buffer's previous frame has been consumed.
+        auto stage = [&](unsigned n2) {                // lane 0 only; n2 = index among this warp's frames
+            const unsigned i2 = (unsigned)w + (unsigned)P * n2;
+            if (i2 >= mine) return;
+            const unsigned rb = (unsigned)w * G::PBUF + (n2 & 1);
+            mbar_expect_tx(&s.rawfull[rb], 3 * N);
+            bulk_g2s(&s.rawb[rb][0], p.adc + frame_of(blockIdx.x + gstride * i2) * (unsigned long long)(3 * N), 3 * N, &s.rawfull[rb]);
+        };
+        if (lane == 0) { stage(0); stage(1); }
+        unsigned mi = (unsigned)w % G::META;            // i % META, kept incrementally
+        for (unsigned n = 0, i = (unsigned)w; i < mine; n++, i += P, mi = mi + P >= G::META ? mi + P - G::META : mi + P) {
+            const unsigned long long f = frame_of(blockIdx.x + gstride * i);
+            PROF_MARK(0);
+            const unsigned pb = (unsigned)w * G::PBUF + (n & 1), pv = n >> 1;
+            uint8_t *const buf = &s.planes[pb][0];
+            const uint8_t *const src = &s.rawb[pb][0];
             const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
+            mbar_wait(&s.rawfull[pb], pv & 1);          // the frame's bytes are in shared memory
 
             // channel sums -> floor mean (rolling_buffer.c:48-64); the sum is rotation invariant
-            uint4 raw[6];
             int mean[3];
+            {
+                unsigned sum[3];
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                unsigned sum = 0;
+                for (int ch = 0; ch < 3; ch++) {
+                    sum[ch] = 0;
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const uint4 x = ldg_stream(src + ch * N + q * 512 + lane * 16);
-                    raw[ch * 2 + q] = x;
-                    sum = __dp4a(x.x, 0x01010101u, sum); sum = __dp4a(x.y, 0x01010101u, sum);
-                    sum = __dp4a(x.z, 0x01010101u, sum); sum = __dp4a(x.w, 0x01010101u, sum);
-                }
-                sum = __reduce_add_sync(0xffffffffu, sum);
-                mean[ch] = (int)(sum >> 10);
-            }
-            {   // next frame of this warp -> L1/L2
-                const unsigned long long fn = f + gstride * P;
-                if (fn < nf && lane * 128 < 3 * N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.adc + fn * (unsigned long long)(3 * N) + lane * 128));
-            }
-            // the tensor core must be done with this warp's previous frame
-            if (v >= 1) mbar_wait(&s.sfree[w], (v - 1) & 1);
-            if (!(p.debug_skip & 1))
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int j0 = q * 512 + lane * 16;
-                    const uint4 x = raw[ch * 2 + q];
-                    const uint32_t rw[4] = {x.x, x.y, x.z, x.w};
-                    if ((head & 15) == 0) {
-                        const int i0 = (j0 - head) & (N - 1);
-                        uint32_t hi[4], lo[4];
-                        umma_prep16(rw, mean[ch], s.win2, i0, hi, lo);
-                        *reinterpret_cast<uint4 *>(plane(0, ch, 0) + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4 *>(plane(0, ch, 1) + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        // second copy, advanced by 8 bytes: sample i sits at PAD - 8 + i
-                        *reinterpret_cast<uint2 *>(plane(1, ch, 0) + PAD - 8 + i0) = make_uint2(hi[0], hi[1]);
-                        *reinterpret_cast<uint2 *>(plane(1, ch, 0) + PAD + i0) = make_uint2(hi[2], hi[3]);
-                        *reinterpret_cast<uint2 *>(plane(1, ch, 1) + PAD - 8 + i0) = make_uint2(lo[0], lo[1]);
-                        *reinterpret_cast<uint2 *>(plane(1, ch, 1) + PAD + i0) = make_uint2(lo[2], lo[3]);
-                    } else {   // ring head not 16-aligned: scalar stores (rare; capture heads are arbitrary)
-#pragma unroll
-                        for (int e = 0; e < 16; e++) {
-                            const int ii = (j0 + e - head) & (N - 1);
-                            const int q24 = imma_prep1(rw[e >> 2] >> (8 * (e & 3)), mean[ch], s.win2, ii) + 0x8000;
-                            const uint8_t hb = (uint8_t)(q24 >> 16), lb = (uint8_t)((q24 >> 8) ^ 0x80);
-                            plane(0, ch, 0)[PAD + ii] = hb; plane(0, ch, 1)[PAD + ii] = lb;
-                            plane(1, ch, 0)[PAD - 8 + ii] = hb; plane(1, ch, 1)[PAD - 8 + ii] = lb;
-                        }
+                    for (int q = 0; q < 2; q++) {
+                        const uint4 x = *reinterpret_cast<const uint4 *>(src + ch * N + q * 512 + lane * 16);
+                        sum[ch] = __dp4a(x.x, 0x01010101u, sum[ch]); sum[ch] = __dp4a(x.y, 0x01010101u, sum[ch]);
+                        sum[ch] = __dp4a(x.z, 0x01010101u, sum[ch]); sum[ch] = __dp4a(x.w, 0x01010101u, sum[ch]);
                     }
                 }
-                if (p.power) {   // rolling_buffer.c:68-70
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) mean[ch] = (int)(__reduce_add_sync(0xffffffffu, sum[ch]) >> 10);
+            }
+            PROF_MARK(1);
+            // the tensor core must be done with the frame that used this plane buffer before
+            if (pv >= 1) mbar_wait(&s.sfree[pb], (pv - 1) & 1);
+            PROF_MARK(2);
+            unsigned sl[3] = {0, 0, 0};
+            auto prep_chunk = [&](int ch, int q, const uint4 x) {
+                const int i0 = q * 512 + lane * 16;
+                const uint32_t rw[4] = {x.x, x.y, x.z, x.w};
+                uint32_t hi[4], lo[4];
+                umma_prep16r(rw, mean[ch], wr[q], hi, lo);
+                AT_CHECK(umma_plane(ch, 1) * PLANE + PAD + i0 + 16 <= G::FRAME);
+                *reinterpret_cast<uint4 *>(buf + umma_plane(ch, 0) * PLANE + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(buf + umma_plane(ch, 1) * PLANE + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                if constexpr (CERT) {
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; w4++) sl[ch] = (unsigned)__dp4a((int)lo[w4], (int)lo[w4], (int)sl[ch]);
+                }
+            };
+            if (!(p.debug_skip & 1)) {
+                if ((head & 15) == 0) {     // the common case, straight-line: chronological chunk = one aligned ring chunk
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++)
+#pragma unroll
+                        for (int q = 0; q < 2; q++)
+                            prep_chunk(ch, q, *reinterpret_cast<const uint4 *>(src + ch * N + ((q * 512 + lane * 16 + head) & (N - 1))));
+                } else {
+#pragma unroll 1
+                    for (int ch = 0; ch < 3; ch++)
+#pragma unroll
+                        for (int q = 0; q < 2; q++) prep_chunk(ch, q, load_chrono16(src + ch * N, q * 512 + lane * 16, head));
+                }
+            }
+            if constexpr (CERT) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) sl[ch] = __reduce_add_sync(0xffffffffu, sl[ch]);
+                if (lane < 3) s.meta[mi][lane] = lane == 0 ? sl[0] : (lane == 1 ? sl[1] : sl[2]);
+            }
+            PROF_MARK(3);
+            if (p.power) {   // rolling_buffer.c:68-70
+                for (int ch = 0; ch < 3; ch++) {
                     long long acc = 0;
-                    for (int k = lane; k < N; k += 32) { const int dv = (int)src[ch * N + k] - mean[ch]; acc += (long long)dv * dv; }
+                    for (int j = lane; j < N; j += 32) { const int dv = (int)src[ch * N + j] - mean[ch]; acc += (long long)dv * dv; }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                     if (lane == 0) p.power[f * 3 + ch] = acc;
@@ -218,95 +327,200 @@ __global__ void __launch_bounds__(512, 1) at_fused_umma_kernel(const AtFusedPara
                 for (int idx = lane; idx < 3 * N; idx += 32) {
                     const int ch = idx / N, ii = idx % N;
                     p.windowed[f * (unsigned long long)(3 * N) + idx] =
-                        (int16_t)((int)(signed char)plane(0, ch, 0)[PAD + ii] * 256 + (int)(signed char)plane(0, ch, 1)[PAD + ii]);
+                        (int16_t)((int)(signed char)buf[umma_plane(ch, 0) * PLANE + PAD + ii] * 256 + (int)(signed char)buf[umma_plane(ch, 1) * PLANE + PAD + ii]);
                 }
             fence_proxy_async();          // this lane's plane bytes -> visible to the tensor core's reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s.ready[w]);
+            __syncwarp();                 // ... and every lane is done reading the staged bytes
+            if (lane == 0) { mbar_arrive(&s.ready[pb]); stage(n + 2); }
+            PROF_MARK(4);
         }
+        PROF_FLUSH(1);
     } else {
         // =================================================================== epilogue sets
-        const int set = (warp - 1 - P) >> 2, wq = warp & 3, tset = wq * 32 + lane;   // tset = TMEM lane = tile row m
-        int *const z = &s.z[set][0][0][0][0];
-        long long *const curve = &s.curve[set][0][0];
-        // TMEM column of the hh tile of each pair (x, y) = (a,b), (a,c), (b,c); hl follows at +16
-        // and (lh, ll) sit OFF_L columns further (the tiles of the y.l plane)
-        for (unsigned long long i = set;; i += G::SETS) {
-            const unsigned long long f = blockIdx.x + gstride * i;
-            if (f >= nf) break;
-            const unsigned u = (unsigned)(i / G::SETS);
-            mbar_wait(&s.full[set], u & 1);
+        const int set = warp >> 2, wq = warp & 3, m = wq * 32 + lane;   // m = TMEM lane = tile row = lag index of n0
+        const bool valid = m >= PAD - L && m <= PAD + L;
+        const bool wants_pos = p.cell || p.xy;
+        const int bar_a = 1 + 2 * set, bar_b = 2 + 2 * set;
+        unsigned par = 0;
+        // CERT: a certified frame whose peak-tuple table entry is still in flight
+        bool pend = false;
+        unsigned long long pend_f = 0;
+        int4 pend_e = make_int4(0, 0, 0, 0);
+        auto flush_pending = [&]() {
+            if (!pend) return;
+            pend = false;
+            if (lane != 0) return;
+            if (pend_e.x >= 0) {
+                if (p.cell) p.cell[pend_f] = pend_e.x;
+                if (p.xy) reinterpret_cast<float2 *>(p.xy)[pend_f] = make_float2(__int_as_float(pend_e.y), __int_as_float(pend_e.z));
+                if (p.stats) { atomicAdd(&p.stats[3], 1ull); atomicAdd(&p.stats[4], 1ull); }
+            } else {
+                p.redo_list[atomicAdd(p.redo_count, 1u)] = (uint32_t)pend_f;     // lags that are no tuple of the LUT: exact search
+            }
+        };
+        PROF_DECL;
+        unsigned slot = (unsigned)set % G::SLOTS, mi = (unsigned)set % G::META;   // i % SLOTS, i % META, kept incrementally
+        for (unsigned n = 0, i = (unsigned)set; i < mine; n++, i += G::SETS, par ^= 1,
+                      slot = (slot + G::SETS) % G::SLOTS, mi = mi + G::SETS >= G::META ? mi + G::SETS - G::META : mi + G::SETS) {
+            const unsigned long long k = blockIdx.x + gstride * i;
+            PROF_MARK(0);
+            mbar_wait(&s.full[set], n & 1);             // full[] is per set (waited in order by that set), empty[] per slot
+            PROF_MARK(1);
             tc_fence_after();
-            if (p.debug_skip & 4) {       // timing experiments: drain the slot without looking at it
+            auto release_slot = [&]() {   // this warp's accumulators are out of TMEM: hand the slot back to the tensor core
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s.empty[set]);
-                continue;
-            }
-            const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + set * G::TCOLS;
+                if (lane == 0) mbar_arrive(&s.empty[slot]);
+            };
+            if (p.debug_skip & 4) { release_slot(); continue; }      // timing experiments: drain the slot without looking at it
+            AT_CHECK(slot * G::TCOLS + (CERT ? 96 : 144) <= 512);
+            const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + slot * G::TCOLS;
+            int (*const spill)[3][32] = s.spill[set][par];
+
+            if constexpr (CERT) {
+                // ---- U = 256 hh + mid of the three pairs, diagonal sums in registers
+                int u0[3], u1[3];
+                {
+                    uint32_t h[16], md[16], h2[16], md2[16];
+                    Arr<16> a;
+                    tmem_ld16(ta + G::col(1, 0), h); tmem_ld16(ta + G::col(1, 1), md);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int pr = 0; pr < 3; pr++) {
-                const uint32_t c_hh = pr == 0 ? 128 : (pr == 1 ? 0 : 32), off_l = pr == 0 ? 32 : 64;
-                uint32_t hh[8], hl[8], lh[8], ll[8];
-                tmem_ld8(ta + c_hh, hh); tmem_ld8(ta + c_hh + 16, hl);
-                tmem_ld8(ta + c_hh + off_l, lh); tmem_ld8(ta + c_hh + off_l + 16, ll);
-                tmem_ld_wait();
-                // transposing scatter: entry (m, phi) belongs to lag index j = m - phi
-                int *const zp = z + pr * 3 * 8 * G::ZP + tset + 7;
+                    for (int j = 0; j < 16; j++) a.v[j] = (int)h[j] * 256 + (int)md[j];
+                    tmem_ld16(ta + G::col(2, 0), h2); tmem_ld16(ta + G::col(2, 1), md2);
+                    diag_butterfly(a, lane, u0[1], u1[1]);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int ph = 0; ph < 8; ph++) {
-                    zp[(0 * 8 + ph) * G::ZP - ph] = (int)hh[ph];
-                    zp[(1 * 8 + ph) * G::ZP - ph] = (int)hl[ph] + (int)lh[ph];
-                    zp[(2 * 8 + ph) * G::ZP - ph] = (int)ll[ph];
+                    for (int j = 0; j < 16; j++) a.v[j] = (int)h2[j] * 256 + (int)md2[j];
+                    tmem_ld16(ta + G::col(0, 0), h); tmem_ld16(ta + G::col(0, 1), md);
+                    diag_butterfly(a, lane, u0[2], u1[2]);
+                    tmem_ld_wait();
+                    release_slot();
+#pragma unroll
+                    for (int j = 0; j < 16; j++) a.v[j] = (int)h[j] * 256 + (int)md[j];
+                    diag_butterfly(a, lane, u0[0], u1[0]);
                 }
-            }
-            tc_fence_before();            // accumulators are out of TMEM: hand the slot back to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s.empty[set]);
-            named_bar(1 + set, 128);
-            // diagonal sums: 9 blocks of 32 lags (3 pairs x 3), block b -> warp b % 4
-            for (int b = wq; b < 9; b += 4) {
-                const int pr = b / 3, j = (b % 3) * 32 + lane;
-                const int *zr = z + pr * 3 * 8 * G::ZP + j + 7;
-                int hh = 0, mid = 0, ll = 0;
+                PROF_MARK(2);
+                if (wq >= 1 && lane >= 17) {
 #pragma unroll
-                for (int ph = 0; ph < 8; ph++) {
-                    hh += zr[(0 * 8 + ph) * G::ZP];
-                    mid += zr[(1 * 8 + ph) * G::ZP];
-                    ll += zr[(2 * 8 + ph) * G::ZP];
+                    for (int pr = 0; pr < 3; pr++) spill[pr][wq - 1][lane] = u1[pr];
                 }
-                const long long val = 65536LL * hh + 256LL * mid + (long long)ll;
-                curve[pr * G::NJ + j] = val;
-                long long key = LLONG_MIN;
-                if (j >= PAD - L && j <= PAD + L) key = val * 128 + (127 - j);   // largest value, then lowest lag
-                key = warp_max_i64(key);
-                if (lane == 0) s.part[set][pr][b % 3] = key;
-            }
-            named_bar(1 + set, 128);
-            if (wq == 0) {
-                int best3[3];
-                long long peak[3];
+                named_bar(bar_a, 128);
+                PROF_MARK(3);
+                if (wq < 3 && lane >= 17) {
+#pragma unroll
+                    for (int pr = 0; pr < 3; pr++) u0[pr] += spill[pr][wq][lane];
+                }
+                // u0[pr] = U of lag index m (complete for every m <= 112).
+                // first-max arg-max of U and its runner-up, per pair (correlations.c:20-23 on C9 = 256 U)
 #pragma unroll
                 for (int pr = 0; pr < 3; pr++) {
-                    long long key = s.part[set][pr][0];
-                    if (s.part[set][pr][1] > key) key = s.part[set][pr][1];
-                    if (s.part[set][pr][2] > key) key = s.part[set][pr][2];
-                    best3[pr] = 127 - (int)(key & 127) - PAD;
-                    peak[pr] = key >> 7;
+                    const int uv = valid ? u0[pr] : INT_MIN;
+                    const int t1 = __reduce_max_sync(0xffffffffu, uv);
+                    const int j1 = __reduce_min_sync(0xffffffffu, (valid && uv == t1) ? m : 0x7fffffff);
+                    const int t2 = __reduce_max_sync(0xffffffffu, m != j1 ? uv : INT_MIN);
+                    if (lane == 0) s.part[set][par][pr][wq] = make_int4(t1, j1, t2, 0);
                 }
-                if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? best3[0] : (lane == 1 ? best3[1] : best3[2]);
-                const bool extras = p.gate || p.raw || p.corr || p.cell || p.highest || p.xy || p.classes;
-                bool settled = !extras;
-                if (extras && !(p.raw || p.corr || p.classes))
-                    settled = peak_tuple_lookup<L>(p, f, lane, best3[0], best3[1], best3[2], peak);
-                if (!settled) epilogue_warp<L, PAD, G::NJ, G::NJ>(curve, best3[0], best3[1], best3[2], s.gauss, p, f, lane);
+                PROF_MARK(4);
+                // The decision rotates over the four quarters; the other three go on to their next frame.
+                if (wq != (int)(n & 3)) { named_bar_arrive(bar_b, 128); continue; }
+                named_bar(bar_b, 128);
+                PROF_MARK(5);
+                flush_pending();
+                const unsigned long long f = frame_of(k);
+                const uint32_t *const sl = s.meta[mi];
+                bool sure = true;
+                int b3[3];
+#pragma unroll
+                for (int pr = 0; pr < 3; pr++) {
+                    const int4 e0 = s.part[set][par][pr][0], e1 = s.part[set][par][pr][1], e2 = s.part[set][par][pr][2], e3 = s.part[set][par][pr][3];
+                    // quarters are in ascending lag order: the first one holding the maximum holds the first-max lag; a
+                    // second quarter holding the same value makes the runner-up equal to the maximum (nothing certified)
+                    const int top = max(max(e0.x, e1.x), max(e2.x, e3.x));
+                    const int qa = e0.x == top ? 0 : (e1.x == top ? 1 : (e2.x == top ? 2 : 3));
+                    const int j1 = qa == 0 ? e0.y : (qa == 1 ? e1.y : (qa == 2 ? e2.y : e3.y));
+                    const int second = max(max(qa == 0 ? e0.z : e0.x, qa == 1 ? e1.z : e1.x), max(qa == 2 ? e2.z : e2.x, qa == 3 ? e3.z : e3.x));
+                    const int xc = pr == 2 ? 1 : 0, yc = pr == 0 ? 1 : 2;
+                    const long long bound = (long long)sqrt_prod_up(sl[xc], sl[yc]) + 1;
+                    sure = sure && 256LL * ((long long)top - (long long)second) > 2 * bound && 256LL * top - bound >= 2048;
+                    b3[pr] = j1 - PAD;
+                }
+                if (sure) {
+                    // certified lags are final; the position comes from the peak-tuple table, whose entry is consumed at
+                    // this warp's next turn (flush_pending) so that the load's latency stays off the chain
+                    if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? b3[0] : (lane == 1 ? b3[1] : b3[2]);
+                    if (lane == 0 && p.gate) p.gate[f] = (b3[0] * b3[0] + b3[1] * b3[1] + b3[2] * b3[2]) > 4 ? 1 : 0;   // sample_compute.h:124-134
+                    if (wants_pos) {
+                        pend_e = __ldg(&p.peak_tab[((b3[0] + L) * (2 * L + 1) + (b3[1] + L)) * (2 * L + 1) + (b3[2] + L)]);
+                        pend_f = f; pend = true;
+                    } else if (lane == 0 && p.stats) atomicAdd(&p.stats[4], 1ull);
+                } else if (lane == 0) {
+                    p.redo_list[atomicAdd(p.redo_count, 1u)] = (uint32_t)f;      // the exact variant finishes this frame
+                }
+                PROF_MARK(6);
+            } else {
+                // ---- exact variant: U = 256 hh + mid and ll of the three pairs; corr = 256 U + ll
+                const unsigned long long f = frame_of(k);
+                long long *const curve = &s.curve[set][0][0];
+                int u0[3], u1[3], l0[3], l1[3];
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const int pr = q == 0 ? 1 : (q == 1 ? 2 : 0);
+                    uint32_t h[16], md[16], ll[16];
+                    tmem_ld16(ta + G::col(pr, 0), h); tmem_ld16(ta + G::col(pr, 1), md); tmem_ld16(ta + G::col(pr, 2), ll);
+                    tmem_ld_wait();
+                    if (q == 2) release_slot();
+                    Arr<16> a, b;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) { a.v[j] = (int)h[j] * 256 + (int)md[j]; b.v[j] = (int)ll[j]; }
+                    diag_butterfly2(a, b, lane, u0[pr], u1[pr], l0[pr], l1[pr]);
+                }
+                PROF_MARK(2);
+                if (wq >= 1 && lane >= 17) {
+#pragma unroll
+                    for (int pr = 0; pr < 3; pr++) { spill[pr][wq - 1][lane] = u1[pr]; spill[3 + pr][wq - 1][lane] = l1[pr]; }
+                }
+                named_bar(bar_a, 128);
+                PROF_MARK(3);
+#pragma unroll
+                for (int pr = 0; pr < 3; pr++) {
+                    if (wq < 3 && lane >= 17) { u0[pr] += spill[pr][wq][lane]; l0[pr] += spill[3 + pr][wq][lane]; }
+                    const long long val = 256LL * (long long)u0[pr] + (long long)l0[pr];
+                    if (m < G::NJ) curve[pr * G::NJ + m] = val;
+                    long long key = valid ? val * 128 + (127 - m) : LLONG_MIN;   // largest value, then lowest lag
+                    key = warp_max_i64(key);
+                    if (lane == 0) s.part64[set][pr][wq] = key;
+                }
+                named_bar(bar_b, 128);
+                PROF_MARK(4);
+                if (wq == 0) {
+                    int best3[3];
+                    long long peak[3];
+#pragma unroll
+                    for (int pr = 0; pr < 3; pr++) {
+                        long long key = s.part64[set][pr][0];
+#pragma unroll
+                        for (int q = 1; q < 4; q++) if (s.part64[set][pr][q] > key) key = s.part64[set][pr][q];
+                        best3[pr] = 127 - (int)(key & 127) - PAD;
+                        peak[pr] = key >> 7;
+                    }
+                    if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? best3[0] : (lane == 1 ? best3[1] : best3[2]);
+                    const bool extras = p.gate || p.raw || p.corr || p.cell || p.highest || p.xy || p.classes;
+                    bool settled = !extras;
+                    if (extras && !(p.raw || p.corr || p.classes))
+                        settled = peak_tuple_lookup<L>(p, f, lane, best3[0], best3[1], best3[2], peak);
+                    if (!settled) epilogue_warp<L, PAD, G::NJ, G::NJ>(curve, best3[0], best3[1], best3[2], s.gauss, p, f, lane);
+                }
+                named_bar(bar_a, 128);      // curve / part64 are rewritten by the next frame of this set
+                PROF_MARK(6);
             }
-            named_bar(1 + set, 128);      // curve / part / z are rewritten by the next frame of this set
         }
+        if constexpr (CERT) flush_pending();
+        PROF_FLUSH(2 + (wq == 0 ? 0 : 1));
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+    if (warp == G::MMAW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
 
 } // namespace atk
@@ -316,23 +530,42 @@ bool at_fused_umma_supports(const AtShape &sh)
     return sh.n_mics == 3 && sh.n_bits == 10 && (sh.max_shift == 46 || sh.max_shift == 44);
 }
 
-template <int L>
-static cudaError_t launch_umma(const AtFusedParams &p, int sm_count, cudaStream_t st)
+// |256 hh + mid| must fit an int32 for every possible frame: |h| <= hmax_i = ((W_i + 128) >> 8) + 1, |l| <= 128
+bool at_fused_umma_window_ok(const int16_t *window, int n)
 {
-    auto kern = atk::at_fused_umma_kernel<L>;
-    const int smem = (int)sizeof(atk::UmmaSmem<L>);
+    long long s2 = 0, s1 = 0;
+    for (int i = 0; i < n; i++) { const long long h = (((long long)window[i] + 128) >> 8) + 1; s2 += h * h; s1 += h; }
+    return 256 * s2 + 2 * 128 * s1 < (1ll << 31);
+}
+
+template <int L, bool CERT>
+static cudaError_t launch_umma(const AtFusedParams &p, unsigned long long work, int sm_count, cudaStream_t st)
+{
+    auto kern = atk::at_fused_umma_kernel<L, CERT>;
+    const int smem = (int)sizeof(atk::UmmaSmem<L, CERT>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     unsigned long long grid = (unsigned long long)sm_count;
-    if (grid > p.n_frames) grid = p.n_frames;
+    if (grid > work) grid = work;
     if (grid == 0) return cudaSuccess;
-    kern<<<(unsigned)grid, 512, smem, st>>>(p);
+    kern<<<(unsigned)grid, atk::UmmaGeo<L, CERT>::THREADS, smem, st>>>(p);
     at_count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t at_launch_fused_umma(const AtShape &sh, const AtFusedParams &p, int sm_count, cudaStream_t st)
+// redo: device scratch of 4 + 4 * n_frames bytes (a counter, zero on entry, followed by the list) or NULL.
+cudaError_t at_launch_fused_umma(const AtShape &sh, const AtFusedParams &p_in, uint32_t *redo, int sm_count, cudaStream_t st)
 {
-    if (p.sig16 || !at_fused_umma_supports(sh)) return cudaErrorInvalidValue;
-    return sh.max_shift == 46 ? launch_umma<46>(p, sm_count, st) : launch_umma<44>(p, sm_count, st);
+    if (p_in.sig16 || !at_fused_umma_supports(sh)) return cudaErrorInvalidValue;
+    AtFusedParams p = p_in;
+    const bool wants_curves = p.raw || p.corr || p.classes || p.highest;
+    const bool cert = redo && !wants_curves && (!(p.cell || p.xy) || p.peak_tab) && !(p.debug_skip & 8) && p.n_frames < (1ull << 32);
+    cudaError_t e;
+    if (!cert) return sh.max_shift == 46 ? launch_umma<46, false>(p, p.n_frames, sm_count, st) : launch_umma<44, false>(p, p.n_frames, sm_count, st);
+    p.redo_count = redo; p.redo_list = redo + 1;
+    e = sh.max_shift == 46 ? launch_umma<46, true>(p, p.n_frames, sm_count, st) : launch_umma<44, true>(p, p.n_frames, sm_count, st);
+    if (e != cudaSuccess) return e;
+    // the frames the certified pass could not settle: exact variant over the list (length read on the device)
+    p.frame_list = redo + 1; p.list_count = redo; p.redo_count = nullptr; p.redo_list = nullptr;
+    return sh.max_shift == 46 ? launch_umma<46, false>(p, p.n_frames, sm_count, st) : launch_umma<44, false>(p, p.n_frames, sm_count, st);
 }

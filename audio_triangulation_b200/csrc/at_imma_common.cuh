@@ -1,5 +1,5 @@
 // at_imma_common.cuh -- device helpers shared by the tensor-core localization kernels
-// (at_fused_imma.cu, at_fused_imma3.cu): IMMA wrappers, byte-wise prep arithmetic, REDUX reductions and
+// (at_fused_imma.cu, at_fused_umma.cu): IMMA wrappers, byte-wise prep arithmetic, REDUX reductions and
 // the warp-scope epilogue (arg-max bookkeeping, Gaussian re-weighting, bounded likelihood search).
 #pragma once
 #include <limits.h>
@@ -93,6 +93,12 @@ __device__ __forceinline__ int imma_prep1(uint32_t raw_byte, int mean, const uin
 {
     const int a = (int)(signed char)((raw_byte - (uint32_t)mean) & 0xFFu);
     return a * (int)(win2[imma_win_index(i)] >> ((i & 1) * 16));
+}
+
+// sqrt(a * b) rounded up (a, b < 2^27): float product and approximate root, both within 2^-20, times 1 + 2^-16
+__device__ __forceinline__ float sqrt_prod_up(unsigned a, unsigned b)
+{
+    return sqrtf((float)a * (float)b) * 1.0000153f + 1.0f;
 }
 
 // 64-bit maximum across the warp with two REDUX instructions (high word signed, low word unsigned).

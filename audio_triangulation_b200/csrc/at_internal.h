@@ -14,6 +14,10 @@ struct AtFusedParams {
     const int16_t *sig16;    // [F][M][N] already prepared frames (drop-in correlations_init path)
     const int32_t *heads;    // [F] or NULL
     unsigned long long n_frames;
+    // tcgen05 kernel of the reference shape only: process the frames named by frame_list[0 .. *list_count) instead of
+    // 0 .. n_frames-1 (the count is read on the device), and / or append the frames it could not settle to redo_list
+    const uint32_t *frame_list; const uint32_t *list_count;
+    uint32_t *redo_list; uint32_t *redo_count;
     // outputs (any may be NULL)
     int32_t *lags;
     void *corr; int32_t corr_struct;
@@ -40,6 +44,7 @@ struct AtFusedParams {
     int32_t debug_skip;      // profiling knob (env AT_DEBUG_SKIP): bit0 skip prep, bit1 skip MMA loop, bit2 skip epilogue
     float px_per_m;
     unsigned long long now_us;
+    unsigned long long *prof; // VARIANT=prof builds only: [4 roles][8 sections] cycle counters (MMA issue, prep, epilogue quarter 0, quarters 1-3)
 };
 
 struct AtShape { int n_mics, n_bits, max_shift; };
@@ -52,12 +57,11 @@ bool at_fused_imma_supports(const AtShape &shape);
 // at_fused_imma_cta.cu -- CTA-per-frame tensor kernel for general arrays (4 / 8 mics, 1024 / 4096 samples)
 cudaError_t at_launch_fused_imma_cta(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
 bool at_fused_imma_cta_supports(const AtShape &shape);
-// at_fused_imma3.cu -- low-instruction-count variant (ldmatrix + delayed plane copies), 1024-sample frames
-cudaError_t at_launch_fused_imma3(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
-bool at_fused_imma3_supports(const AtShape &shape);
 
 // at_fused_umma.cu -- tcgen05 (UMMA) polyphase kernel, 3 mics x 1024 samples
-cudaError_t at_launch_fused_umma(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
+// redo: device scratch of 4 * (n_frames + 1) bytes whose first word is zero (certified pass + exact pass over its list), or NULL
+cudaError_t at_launch_fused_umma(const AtShape &shape, const AtFusedParams &p, uint32_t *redo, int sm_count, cudaStream_t st);
+bool at_fused_umma_window_ok(const int16_t *window, int n);
 bool at_fused_umma_supports(const AtShape &shape);
 // at_fused_umma_m.cu -- tcgen05 (UMMA) kernel for 8-microphone arrays, 1024 / 4096 samples
 cudaError_t at_launch_fused_umma_m(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);

@@ -59,6 +59,10 @@ __device__ __forceinline__ void named_bar(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
+{
+    asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ int dp2a_lo_acc(uint32_t a, uint32_t b, int c)
 {
     int r;
@@ -92,12 +96,75 @@ __device__ __forceinline__ void umma_prep16(const uint32_t (&rw)[4], int mean, c
         hi[w4] = __byte_perm(t01, t23, 0x7632);
     }
 }
+// the same with the lane's 16 window words (doubled, pre-masked: even samples low half, odd samples high half) in registers
+__device__ __forceinline__ void umma_prep16r(const uint32_t (&rw)[4], int mean, const uint32_t (&wr)[16],
+                                             uint32_t (&hi)[4], uint32_t (&lo)[4])
+{
+    const uint32_t k4 = (uint32_t)((256 - mean) & 0xFF) * 0x01010101u;
+    const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
+#pragma unroll
+    for (int w4 = 0; w4 < 4; w4++) {
+        const uint32_t d = sub_bytes(rw[w4], k7, kM);
+        const int p0 = dp2a_lo_acc(wr[4 * w4 + 0], d, 0x8000), p1 = dp2a_lo_acc(wr[4 * w4 + 1], d, 0x8000);
+        const int p2 = dp2a_hi_acc(wr[4 * w4 + 2], d, 0x8000), p3 = dp2a_hi_acc(wr[4 * w4 + 3], d, 0x8000);
+        const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
+        const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
+        lo[w4] = __byte_perm(t01, t23, 0x5410) ^ 0x80808080u;
+        hi[w4] = __byte_perm(t01, t23, 0x7632);
+    }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
+}
+
+// ---------------------------------------------------------------- diagonal sums of a polyphase tile, in registers
+// A 32-row x 16-phase block held one row per lane (tcgen05.ld 32x32b: lane = row, register = phase): entry
+// (row, phi) belongs to lag index row - phi.  Five exchange stages (lane ^ 1, 2, 4, 8, 16): in stage k a lane sends the
+// odd entries of its array to its partner and keeps the even ones, so that afterwards it holds the lags congruent to
+// itself modulo 2^(k+1); the upper lane of a pair sees its partner's entries one slot later (its row is 2^k higher).
+// 16 shuffles per block.  Result: n0 = sum for lag index (lane), n1 = partial sum for lag index (lane - 32), non-zero
+// for lanes >= 17 only -- the 15 lags whose rows straddle two lane quarters.  (tools/probes/epi_probe.cu checks it.)
+template <int N>
+struct Arr { int v[N]; };
+template <int N, int K>
+__device__ __forceinline__ Arr<N / 2 + 1> bfly_stage(const Arr<N> &in, int lane)
+{
+    constexpr int NE = N / 2, NO = N / 2 + 1;
+    const bool upper = (lane >> K) & 1;
+    int r[NE];
+#pragma unroll
+    for (int s = 0; s < NE; s++) r[s] = __shfl_xor_sync(0xffffffffu, in.v[2 * s + 1], 1 << K);
+    Arr<NO> out;
+#pragma unroll
+    for (int s = 0; s < NO; s++) {
+        const int base = 2 * s < N ? in.v[2 * s] : 0;
+        const int lo = s < NE ? r[s] : 0, up = s >= 1 ? r[s - 1] : 0;
+        out.v[s] = base + (upper ? up : lo);
+    }
+    return out;
+}
+__device__ __forceinline__ void diag_butterfly(const Arr<16> &a, int lane, int &n0, int &n1)
+{
+    const Arr<9> b = bfly_stage<16, 0>(a, lane);
+    const Arr<5> c = bfly_stage<9, 1>(b, lane);
+    const Arr<3> d = bfly_stage<5, 2>(c, lane);
+    const Arr<2> e = bfly_stage<3, 3>(d, lane);
+    const Arr<2> f = bfly_stage<2, 4>(e, lane);
+    n0 = f.v[0]; n1 = f.v[1];
+}
+// two independent blocks, stages interleaved (twice the shuffles in flight per warp)
+__device__ __forceinline__ void diag_butterfly2(const Arr<16> &a, const Arr<16> &a2, int lane, int &n0, int &n1, int &p0, int &p1)
+{
+    const Arr<9> b = bfly_stage<16, 0>(a, lane), b2 = bfly_stage<16, 0>(a2, lane);
+    const Arr<5> c = bfly_stage<9, 1>(b, lane), c2 = bfly_stage<9, 1>(b2, lane);
+    const Arr<3> d = bfly_stage<5, 2>(c, lane), d2 = bfly_stage<5, 2>(c2, lane);
+    const Arr<2> e = bfly_stage<3, 3>(d, lane), e2 = bfly_stage<3, 3>(d2, lane);
+    const Arr<2> f = bfly_stage<2, 4>(e, lane), f2 = bfly_stage<2, 4>(e2, lane);
+    n0 = f.v[0]; n1 = f.v[1]; p0 = f2.v[0]; p1 = f2.v[1];
 }
 
 } // namespace atk

@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_DEFAULT, help="frames per GPU per step")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "imma", "imma_lm", "umma"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "imma", "umma"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

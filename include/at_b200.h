@@ -118,9 +118,9 @@ uint64_t at_get_time_us(void);
 #define AT_KERNEL_AUTO 0
 #define AT_KERNEL_IMAD 1  /* IMAD.WIDE register-tiled direct form (integer pipe) */
 #define AT_KERNEL_IMMA 2  /* byte-split Toeplitz x Hankel int8 tensor-core form (exact) */
-#define AT_KERNEL_IMMA_LM 3 /* same, fragments via ldmatrix + delayed plane copies (fewest instructions; N = 1024) */
-#define AT_KERNEL_UMMA 4  /* polyphase Hankel form on tcgen05 (UMMA, TMEM accumulators), exact; 3 mics x 1024 samples,
-                             8 mics x 1024 / 4096 samples (AUTO picks it for 8 x 4096) */
+/* 3 was an ldmatrix variant of AT_KERNEL_IMMA; removed in round 2 (never faster) */
+#define AT_KERNEL_UMMA 4  /* polyphase Hankel form on tcgen05 (UMMA, TMEM accumulators), exact; 3 mics x 1024 samples
+                             (AUTO picks it: the reference shape), 8 mics x 1024 / 4096 samples (AUTO picks it for 8 x 4096) */
 
 /* layout of the optional correlation-curve output */
 #define AT_CORR_PACKED 0  /* int64 [F][pairs][2L+1] */
@@ -198,7 +198,9 @@ int at_synchronize(at_context *ctx);
 /* Temporal stage for `n_arrays` independent arrays (ref: sample_compute.h:124-139,
  * correlations.c:38-63): where gate[i] != 0, estimate <- EMA(estimate, fresh) with the array's own
  * last_update, re-arg-max, stamp now_us.  est/fresh: struct-of-arrays, int64 [A][pairs][2L+1];
- * est_best int32 [A][pairs]; est_time uint64 [A][pairs]. Device pointers. */
+ * est_best int32 [A][pairs]; est_time uint64 [A][pairs]. Device pointers.  The decay factor 1 - exp(-dt/0.5) is
+ * evaluated on the host with the reference's own libm call (the time stamps are read back, which synchronises
+ * `stream` once), so the averaged curves are the reference's bit for bit. */
 int at_average_device(at_context *ctx, int64_t *d_est, int32_t *d_est_best, uint64_t *d_est_time,
                       const int64_t *d_fresh, const uint8_t *d_gate, size_t n_arrays, uint64_t now_us,
                       void *stream);

@@ -36,6 +36,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_hm():
+    """Lag LUT and per-cell colour classes produced by the reference's own vga_heatmap.h (tests/golden/make_heatmap_golden.py)."""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_heatmap.npz"))
+
+
+@pytest.fixture(scope="session")
 def loc():
     """Reference-shape Localizer on cuda:0 (GPU tests only)."""
     import torch

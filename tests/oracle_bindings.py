@@ -62,6 +62,8 @@ def load_oracle():
     lib.ato_lut_build.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                   C.c_float, C.c_float, u8p]
     lib.ato_heatmap.argtypes = [i64p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ato_synth_frames.argtypes = [C.c_uint64, C.c_uint32, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.ato_synth_plain.argtypes = [C.c_int]
     lib.ato_localize.argtypes = [C.POINTER(AtoConfig), u8p, C.c_void_p, C.c_size_t,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     return lib
@@ -137,6 +139,14 @@ class Oracle:
         self.lib.ato_lut_build(self.mics().reshape(-1), 3, self.L, RATE_HZ, SPEED, HALF_W, HALF_H,
                                PX_PER_M, HEIGHT, idx.reshape(-1))
         return idx.reshape(3, -1)
+
+    def synth(self, n_frames, seed=0xA7D10, flags=0, first_frame=0, nthreads=0):
+        """Frames of the bench workload generated on the host without the product library (oracle/synth_host.cpp)."""
+        adc = np.empty((n_frames, 3, N), np.uint8)
+        heads = np.zeros(n_frames, np.int32); cell = np.zeros(n_frames, np.int32)
+        self.lib.ato_synth_frames(seed, flags, first_frame, n_frames, adc.ctypes.data, heads.ctypes.data, cell.ctypes.data,
+                                  nthreads or (os.cpu_count() or 1))
+        return adc, heads, cell
 
     def localize(self, adc, heads=None, want_corr=True, want_raw=False, want_cell=True, nthreads=1):
         adc = np.ascontiguousarray(adc, np.uint8)

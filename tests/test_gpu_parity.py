@@ -13,7 +13,7 @@ from oracle_bindings import CELLS, CORR_DT, HALF_H, HALF_W, HEIGHT, PX_PER_M, RA
 pytestmark = pytest.mark.gpu
 
 ALL = ("lags", "corr", "raw", "cell", "highest", "xy", "gate", "classes", "windowed", "power")
-KERNELS = ("imad", "imma", "imma_lm", "umma")
+KERNELS = ("imad", "imma", "umma")
 
 
 def _torch():
@@ -226,7 +226,74 @@ def test_dropin_average_chain(golden):
         assert est[p]["best_shift"][0] == golden["avg_best"][p] and est[p]["last_update"][0] == golden["avg_last"][p]
 
 
+def test_oracle_synth_equals_product_synth(loc, oracle):
+    """bench.py's reference arm generates its inputs with oracle/synth_host.cpp (it must not map the product library);
+    they are the product generator's frames byte for byte, on the device and on the host."""
+    torch = _torch()
+    F = 3000
+    for flags in (0, 2 | 4, 1):
+        adc, heads, cell = loc.synth_device(F, flags=flags, first_frame=12345)
+        torch.cuda.synchronize()
+        o_adc, o_heads, o_cell = oracle.synth(F, flags=flags, first_frame=12345)
+        assert (adc.cpu().numpy() == o_adc).all() and (heads.cpu().numpy() == o_heads).all() and (cell.cpu().numpy() == o_cell).all()
+
+
+# ---------------------------------------------------------------- a19 / a20 against the reference's own vga_heatmap.h
+def test_lut_and_classes_equal_reference_heatmap_code(loc, golden, golden_hm):
+    """tests/golden/ref_heatmap.npz was produced by vga_init_heatmap / vga_draw_heatmap compiled unmodified
+    (oracle/hm_host.c).  The device-built geometry and look-up table, the stand-alone likelihood map and the fused
+    kernel's `classes` output must reproduce the reference's table and its colour of every cell."""
+    torch = _torch()
+    assert (loc.mics().view(np.uint32) == golden_hm["mics"].view(np.uint32)).all()
+    assert (loc.lut().reshape(3, -1) == golden_hm["lut"]).all()
+    curves = golden_hm["curves"]
+    hm = loc.heatmap_device(torch.from_numpy(curves).cuda(), want=("cell", "highest", "classes"))
+    torch.cuda.synchronize()
+    assert (hm["classes"].cpu().numpy() == golden_hm["classes"]).all()
+    lut = golden_hm["lut"]
+    like = curves[:, 0][:, lut[0]] + curves[:, 1][:, lut[1]] + curves[:, 2][:, lut[2]]          # [K][cells]
+    assert (hm["highest"].cpu().numpy() == like.max(axis=1)).all() and (hm["cell"].cpu().numpy() == like.argmax(axis=1)).all()
+    # the fused kernel on the golden frames: its per-frame curves are golden["corr"] = golden_hm["curves"][:K]
+    K = golden["adc"].shape[0]
+    assert (curves[:K] == golden["corr"]).all()
+    got = loc.localize_device(torch.from_numpy(golden["adc"]).cuda(), want=("classes", "cell", "highest"))
+    torch.cuda.synchronize()
+    assert (got["classes"].cpu().numpy() == golden_hm["classes"][:K]).all()
+    assert (got["cell"].cpu().numpy() == like[:K].argmax(axis=1)).all() and (got["highest"].cpu().numpy() == like[:K].max(axis=1)).all()
+
+
 # ---------------------------------------------------------------- temporal stage + map on device arrays
+def test_average_device_many_dt(loc, oracle, golden):
+    """120 000 random time differences (microseconds to minutes): the batched EMA equals the reference formula
+    (correlations.c:42-49, host libm) bit for bit for every one of them, gated arrays untouched."""
+    torch = _torch()
+    n_kat = len(golden["kat_names"])
+    A = 40_000
+    rng = np.random.default_rng(77)
+    pick = rng.integers(n_kat, golden["adc"].shape[0], (2, A))
+    est = golden["corr"][pick[0]].copy(); fresh = golden["corr"][pick[1]].copy()
+    now = 200_000_000
+    scale = 10.0 ** rng.uniform(0, 8.3, (A, 3))                   # dt from 1 us to 200 s
+    times = (now - np.minimum(scale, now).astype(np.uint64)).astype(np.uint64)
+    times[:100] = now                                              # dt = 0
+    times[100:200, :] = times[100:200, :1]                         # arrays whose pairs share their stamp
+    gate = (rng.random(A) > 0.1).astype(np.uint8)
+    d_est = torch.from_numpy(est).cuda(); d_best = torch.zeros((A, 3), dtype=torch.int32, device="cuda")
+    d_time = torch.from_numpy(times.view(np.int64)).cuda()
+    loc.average_device(d_est, d_best, d_time, torch.from_numpy(fresh).cuda(), torch.from_numpy(gate).cuda(), now)
+    torch.cuda.synchronize()
+    exp = est.copy(); exp_best = np.zeros((A, 3), np.int32)
+    lib = oracle.lib
+    for a in np.nonzero(gate)[0]:
+        for p in range(3):
+            t = C.c_uint64(int(times[a, p]))
+            lib.ato_average(exp[a, p], exp_best[a, p:p + 1], C.byref(t), fresh[a, p], L, now)
+    got = d_est.cpu().numpy()
+    bad = np.nonzero((got != exp).any(axis=2))
+    assert bad[0].size == 0, f"{bad[0].size} (array, pair) entries differ, first: array {bad[0][0]} pair {bad[1][0]}"
+    assert (d_best.cpu().numpy()[gate == 1] == exp_best[gate == 1]).all()
+
+
 def test_average_and_heatmap_device(loc, oracle, golden):
     torch = _torch()
     n_kat = len(golden["kat_names"])
@@ -250,7 +317,7 @@ def test_average_and_heatmap_device(loc, oracle, golden):
             oracle.lib.ato_average(exp[a, p], exp_best[a, p:p + 1], C.byref(t), np.ascontiguousarray(fresh[a, p]), L, now)
             exp_time[a, p] = t.value
     got = d_est.cpu().numpy()
-    assert (got == exp).all()            # device double exp vs glibc: see DESIGN.md (bit-equal here)
+    assert (got == exp).all()            # decay factors come from the host libm: bit-equal by construction
     assert (d_best.cpu().numpy()[gate == 1] == exp_best[gate == 1]).all()
     assert (d_time.cpu().numpy().view(np.uint64) == exp_time).all()
     hm = loc.heatmap_device(torch.from_numpy(exp).cuda(), want=("cell", "highest", "xy", "classes"))

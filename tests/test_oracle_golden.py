@@ -105,3 +105,42 @@ def test_heatmap_definition(oracle):
     exp = np.where(like >= (top * 63) >> 6, 15, np.where(like >= (top * 31) >> 5, 3,
                    np.where(like >= (top * 15) >> 4, 8, np.where(like >= (top * 7) >> 3, 5, 0))))
     assert (cls == exp).all()
+
+
+# ---------------------------------------------------------------- a19 / a20 pinned to the reference's own vga_heatmap.h
+def test_lut_is_the_reference_lut(oracle, golden_hm):
+    """vga_init_heatmap (vga_heatmap.h:48-93), compiled unmodified, built golden_hm['lut']; the restated ato_lut_build and
+    ato_mics_triangle must reproduce it and the reference's microphone coordinates exactly."""
+    assert golden_hm["dims"].tolist() == [101, 101, NL]
+    assert golden_hm["colors"].tolist() == [15, 3, 8, 5, 0]               # WHITE GREEN RED BLUE BLACK (vga16_graphics.h:31-34)
+    assert (oracle.mics().view(np.uint32) == golden_hm["mics"].view(np.uint32)).all()
+    assert (oracle.reference_lut() == golden_hm["lut"]).all()
+
+
+def test_classes_are_the_reference_classes(oracle, golden_hm):
+    """vga_draw_heatmap (vga_heatmap.h:95-135) coloured every cell for 41 curve triples (golden frames, the EMA estimate,
+    edge cases: silence, negative maxima, ties, peaks outside the LUT); ato_heatmap must give the same class per cell,
+    and its highest_L / first cell must be consistent with the reference's look-up table."""
+    lut = np.ascontiguousarray(golden_hm["lut"])
+    for k in range(golden_hm["curves"].shape[0]):
+        corr = np.ascontiguousarray(golden_hm["curves"][k])
+        hi = np.zeros(1, np.int64); cell = np.zeros(1, np.int32); cls = np.zeros(CELLS, np.uint8)
+        oracle.lib.ato_heatmap(corr.reshape(-1), lut.reshape(-1), 3, CELLS, L, hi.ctypes.data, cell.ctypes.data, cls.ctypes.data)
+        assert (cls == golden_hm["classes"][k]).all(), f"curve set {k}"
+        like = corr[0][lut[0]] + corr[1][lut[1]] + corr[2][lut[2]]
+        assert hi[0] == like.max() and cell[0] == int(np.argmax(like))
+
+
+def test_host_generator_self_consistent(oracle):
+    """oracle/synth_host.cpp tabulates the source sequence per frame; the bytes must equal the plain per-byte evaluation of
+    the generator header (at_synth.h), known-answer frames and random ring heads included, whatever the thread count."""
+    a, ha, ca = oracle.synth(600, flags=2 | 4, nthreads=3)
+    oracle.lib.ato_synth_plain(1)
+    try:
+        b, hb, cb = oracle.synth(600, flags=2 | 4, nthreads=1)
+    finally:
+        oracle.lib.ato_synth_plain(0)
+    assert (a == b).all() and (ha == hb).all() and (ca == cb).all()
+    assert (a[0, 0] == 128).all() and (a[0, 1] == 131).all()          # frame 0 = the silence KAT (SURVEY 4)
+    c, _, _ = oracle.synth(100, first_frame=500, flags=2 | 4)
+    assert (c == a[500:]).all()                                       # counter-based: any sub-range gives the same frames

@@ -4,7 +4,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import audio_triangulation_b200 as at
 ALL = ("lags", "corr", "raw", "cell", "highest", "xy", "gate", "classes", "windowed", "power")
-for kernel in ("imma", "imma_lm", "umma", "imad"):
+for kernel in ("imma", "umma", "imad"):
     loc = at.Localizer(kernel=kernel)
     adc, heads, _ = loc.synth_device(67, flags=2 | 4)
     r = loc.localize_device(adc, heads, want=ALL)
