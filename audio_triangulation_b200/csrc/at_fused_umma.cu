@@ -75,13 +75,15 @@ struct UmmaGeo {
     static constexpr int FRAME = NPLANES * PLANE;       // 6 912 bytes of planes per frame
     static constexpr int NJ = 96;                       // lag slots kept (j = 0..95), j in [PAD-L, PAD+L] are real
     static constexpr int NL = 2 * L + 1;
-    static constexpr int TCOLS = CERT ? 96 : 160;       // TMEM columns per accumulator slot (96 / 144 used)
-    static constexpr int SLOTS = CERT ? 5 : 3;
+    static constexpr int TCOLS = CERT ? 128 : 160;      // TMEM columns per accumulator slot (96 / 144 used)
+    // Accumulator slots in TMEM.  Their number must not divide SETS: frame i then re-uses the slot of frame i - SLOTS, which
+    // another epilogue set has drained, and the tensor core can work one frame ahead of every set.
+    static constexpr int SLOTS = CERT ? 4 : 3;
     static constexpr int PREP_WARPS = 7, PBUF = 2, SETS = 5, META = 32;
     static constexpr int THREADS = 32 * (1 + PREP_WARPS + 4 * SETS);
     static_assert(PAD >= L && PAD + L + 15 < 128 && PAD + L < NJ, "lag window must fit the 128-row tile");
     static_assert(127 + 16 * 63 + 16 <= PLANE, "A operand reads stay inside a plane buffer");
-    static_assert(SLOTS * TCOLS <= 512, "TMEM columns");
+    static_assert(SLOTS * TCOLS <= 512 && SETS % SLOTS != 0, "TMEM columns / slot rotation");
     static constexpr int PREP0 = 4 * SETS, MMAW = PREP0 + PREP_WARPS;   // first prep warp, MMA warp (epilogue warp w owns TMEM lane quarter w % 4)
     static_assert(META >= PREP_WARPS * PBUF + SLOTS + SETS, "meta ring must outlive every frame in flight");
     // first TMEM column (within a slot) of the hh (0) / mid (1) / ll (2) tile of pair 0 = (a,b), 1 = (a,c), 2 = (b,c)
@@ -99,10 +101,13 @@ struct UmmaSmem {
     using G = UmmaGeo<L, CERT>;
     alignas(128) uint8_t planes[G::PREP_WARPS * G::PBUF][G::FRAME];
     alignas(128) uint8_t rawb[G::PREP_WARPS * G::PBUF][3 * G::N];   // ring-ordered ADC bytes, staged by bulk copies (TMA)
-    alignas(16) long long curve[CERT ? 1 : G::SETS][3][G::NJ];   // exact raw curves by lag index (input of epilogue_warp)
-    alignas(16) long long part64[G::SETS][3][4];        // exact variant: per-warp arg-max keys
-    alignas(16) int4 part[G::SETS][2][3][4];            // CERT: per-warp {max, arg-max, runner-up}
-    alignas(16) int spill[G::SETS][2][6][3][32];        // partial sums that cross a lane quarter: [array][quarter below][lane]
+    // CERT: diagonal sums of the three pairs by lag index, [set][frame parity][n0 | n1][pair][lag index]; the n1 entries no
+    // quarter ever writes stay zero from the kernel's start
+    alignas(16) int ubuf[CERT ? G::SETS : 1][2][2][3][128];
+    // exact variant
+    alignas(16) long long curve[CERT ? 1 : G::SETS][3][G::NJ];   // raw curves by lag index (input of epilogue_warp)
+    alignas(16) long long part64[CERT ? 1 : G::SETS][3][4];      // per-warp arg-max keys
+    alignas(16) int spill[CERT ? 1 : G::SETS][2][6][3][32];      // partial sums that cross a lane quarter: [array][quarter below][lane]
     alignas(16) uint32_t meta[G::META][4];              // per frame: sum of squared low digits of each channel
     float gauss[2 * L + 1];
     alignas(8) uint64_t full[G::SETS], empty[G::SLOTS], ready[G::PREP_WARPS * G::PBUF], sfree[G::PREP_WARPS * G::PBUF],
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
     // ---- one-time CTA set-up: zero the planes (pads stay zero), Gaussian factors, barriers, TMEM
     for (int i = tid; i < (int)(sizeof(s.planes) / 16); i += G::THREADS)
         reinterpret_cast<uint4 *>(&s.planes[0][0])[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(sizeof(s.ubuf) / 4); i += G::THREADS) (&s.ubuf[0][0][0][0][0])[i] = 0;
     for (int i = tid; i < 2 * L + 1; i += G::THREADS) s.gauss[i] = p.gauss[i];
     if (tid == 0) {
         for (int k = 0; k < G::SETS; k++) mbar_init(&s.full[k], 1);
@@ -258,7 +264,10 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
             const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
             mbar_wait(&s.rawfull[pb], pv & 1);          // the frame's bytes are in shared memory
 
-            // channel sums -> floor mean (rolling_buffer.c:48-64); the sum is rotation invariant
+            // channel sums -> floor mean (rolling_buffer.c:48-64); the sum is rotation invariant.  With a 16-aligned head the
+            // lane's ring chunks ARE its chronological chunks (rotated): they stay in registers for the second pass.
+            const bool aligned = (head & 15) == 0;
+            uint4 raw[6];
             int mean[3];
             {
                 unsigned sum[3];
@@ -267,7 +276,8 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                     sum[ch] = 0;
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
-                        const uint4 x = *reinterpret_cast<const uint4 *>(src + ch * N + q * 512 + lane * 16);
+                        const uint4 x = *reinterpret_cast<const uint4 *>(src + ch * N + ((q * 512 + lane * 16 + (aligned ? head : 0)) & (N - 1)));
+                        raw[ch * 2 + q] = x;
                         sum[ch] = __dp4a(x.x, 0x01010101u, sum[ch]); sum[ch] = __dp4a(x.y, 0x01010101u, sum[ch]);
                         sum[ch] = __dp4a(x.z, 0x01010101u, sum[ch]); sum[ch] = __dp4a(x.w, 0x01010101u, sum[ch]);
                     }
@@ -294,12 +304,11 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 }
             };
             if (!(p.debug_skip & 1)) {
-                if ((head & 15) == 0) {     // the common case, straight-line: chronological chunk = one aligned ring chunk
+                if (aligned) {              // the common case, straight-line, from registers
 #pragma unroll
                     for (int ch = 0; ch < 3; ch++)
 #pragma unroll
-                        for (int q = 0; q < 2; q++)
-                            prep_chunk(ch, q, *reinterpret_cast<const uint4 *>(src + ch * N + ((q * 512 + lane * 16 + head) & (N - 1))));
+                        for (int q = 0; q < 2; q++) prep_chunk(ch, q, raw[ch * 2 + q]);
                 } else {
 #pragma unroll 1
                     for (int ch = 0; ch < 3; ch++)
@@ -340,23 +349,24 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
         const int set = warp >> 2, wq = warp & 3, m = wq * 32 + lane;   // m = TMEM lane = tile row = lag index of n0
         const bool valid = m >= PAD - L && m <= PAD + L;
         const bool wants_pos = p.cell || p.xy;
-        const int bar_a = 1 + 2 * set, bar_b = 2 + 2 * set;
+        const int bar_a = 1 + 2 * set, bar_b = 2 + 2 * set;      // exact variant
         unsigned par = 0;
-        // CERT: a certified frame whose peak-tuple table entry is still in flight
-        bool pend = false;
+        // CERT: a certified frame whose peak-tuple table entry has been prefetched but not read yet
+        int pend_idx = -1;
         unsigned long long pend_f = 0;
-        int4 pend_e = make_int4(0, 0, 0, 0);
         auto flush_pending = [&]() {
-            if (!pend) return;
-            pend = false;
-            if (lane != 0) return;
-            if (pend_e.x >= 0) {
-                if (p.cell) p.cell[pend_f] = pend_e.x;
-                if (p.xy) reinterpret_cast<float2 *>(p.xy)[pend_f] = make_float2(__int_as_float(pend_e.y), __int_as_float(pend_e.z));
-                if (p.stats) { atomicAdd(&p.stats[3], 1ull); atomicAdd(&p.stats[4], 1ull); }
-            } else {
-                p.redo_list[atomicAdd(p.redo_count, 1u)] = (uint32_t)pend_f;     // lags that are no tuple of the LUT: exact search
+            if (pend_idx < 0) return;
+            if (lane == 0) {
+                const int4 e = __ldg(&p.peak_tab[pend_idx]);
+                if (e.x >= 0) {
+                    if (p.cell) p.cell[pend_f] = e.x;
+                    if (p.xy) reinterpret_cast<float2 *>(p.xy)[pend_f] = make_float2(__int_as_float(e.y), __int_as_float(e.z));
+                    if (p.stats) { atomicAdd(&p.stats[3], 1ull); atomicAdd(&p.stats[4], 1ull); }
+                } else {
+                    p.redo_list[atomicAdd(p.redo_count, 1u)] = (uint32_t)pend_f;     // lags that are no tuple of the LUT: exact search
+                }
             }
+            pend_idx = -1;
         };
         PROF_DECL;
         unsigned slot = (unsigned)set % G::SLOTS, mi = (unsigned)set % G::META;   // i % SLOTS, i % META, kept incrementally
@@ -373,59 +383,52 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 if (lane == 0) mbar_arrive(&s.empty[slot]);
             };
             if (p.debug_skip & 4) { release_slot(); continue; }      // timing experiments: drain the slot without looking at it
-            AT_CHECK(slot * G::TCOLS + (CERT ? 96 : 144) <= 512);
+            AT_CHECK(slot * G::TCOLS + (CERT ? 96 : 144) <= 512 && slot < G::SLOTS);
             const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + slot * G::TCOLS;
-            int (*const spill)[3][32] = s.spill[set][par];
 
             if constexpr (CERT) {
                 // ---- U = 256 hh + mid of the three pairs, diagonal sums in registers
                 int u0[3], u1[3];
                 {
-                    uint32_t h[16], md[16], h2[16], md2[16];
-                    Arr<16> a;
-                    tmem_ld16(ta + G::col(1, 0), h); tmem_ld16(ta + G::col(1, 1), md);
-                    tmem_ld_wait();
+                    // all six tiles leave TMEM before the first butterfly, so that the slot goes back to the tensor core early
+                    Arr<16> a1, a2, a0;
+                    {
+                        uint32_t h[16], md[16], h2[16], md2[16];
+                        tmem_ld16(ta + G::col(1, 0), h); tmem_ld16(ta + G::col(1, 1), md);
+                        tmem_ld16(ta + G::col(2, 0), h2); tmem_ld16(ta + G::col(2, 1), md2);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; j++) a.v[j] = (int)h[j] * 256 + (int)md[j];
-                    tmem_ld16(ta + G::col(2, 0), h2); tmem_ld16(ta + G::col(2, 1), md2);
-                    diag_butterfly(a, lane, u0[1], u1[1]);
-                    tmem_ld_wait();
+                        for (int j = 0; j < 16; j++) { a1.v[j] = (int)h[j] * 256 + (int)md[j]; a2.v[j] = (int)h2[j] * 256 + (int)md2[j]; }
+                        tmem_ld16(ta + G::col(0, 0), h); tmem_ld16(ta + G::col(0, 1), md);
+                        tmem_ld_wait();
+                        release_slot();
 #pragma unroll
-                    for (int j = 0; j < 16; j++) a.v[j] = (int)h2[j] * 256 + (int)md2[j];
-                    tmem_ld16(ta + G::col(0, 0), h); tmem_ld16(ta + G::col(0, 1), md);
-                    diag_butterfly(a, lane, u0[2], u1[2]);
-                    tmem_ld_wait();
-                    release_slot();
+                        for (int j = 0; j < 16; j++) a0.v[j] = (int)h[j] * 256 + (int)md[j];
+                    }
+                    if (p.debug_skip & 32) {     // timing experiments: no diagonal sums
 #pragma unroll
-                    for (int j = 0; j < 16; j++) a.v[j] = (int)h[j] * 256 + (int)md[j];
-                    diag_butterfly(a, lane, u0[0], u1[0]);
+                        for (int pr = 0; pr < 3; pr++) { u0[pr] = a1.v[pr] ^ a2.v[pr + 3] ^ a0.v[pr + 6]; u1[pr] = a1.v[pr + 9] + a2.v[pr + 12] + a0.v[15 - pr]; }
+                    } else {
+                        diag_butterfly2(a1, a2, lane, u0[1], u1[1], u0[2], u1[2]);
+                        diag_butterfly(a0, lane, u0[0], u1[0]);
+                    }
                 }
                 PROF_MARK(2);
-                if (wq >= 1 && lane >= 17) {
-#pragma unroll
-                    for (int pr = 0; pr < 3; pr++) spill[pr][wq - 1][lane] = u1[pr];
-                }
-                named_bar(bar_a, 128);
-                PROF_MARK(3);
-                if (wq < 3 && lane >= 17) {
-#pragma unroll
-                    for (int pr = 0; pr < 3; pr++) u0[pr] += spill[pr][wq][lane];
-                }
-                // u0[pr] = U of lag index m (complete for every m <= 112).
-                // first-max arg-max of U and its runner-up, per pair (correlations.c:20-23 on C9 = 256 U)
+                // Every quarter leaves its sums in shared memory: n0 = lag index m (complete up to the rows of the next
+                // quarter) and, lanes >= 17, n1 = the part of lag index m - 32 that this quarter's rows hold.  One warp per
+                // frame -- the role rotates over the four quarters -- adds the two, finds the arg-max and decides; the other
+                // three arrive on the barrier and go on to their next frame.
+                int (*const ub)[3][128] = s.ubuf[set][par];
 #pragma unroll
                 for (int pr = 0; pr < 3; pr++) {
-                    const int uv = valid ? u0[pr] : INT_MIN;
-                    const int t1 = __reduce_max_sync(0xffffffffu, uv);
-                    const int j1 = __reduce_min_sync(0xffffffffu, (valid && uv == t1) ? m : 0x7fffffff);
-                    const int t2 = __reduce_max_sync(0xffffffffu, m != j1 ? uv : INT_MIN);
-                    if (lane == 0) s.part[set][par][pr][wq] = make_int4(t1, j1, t2, 0);
+                    ub[0][pr][m] = u0[pr];
+                    if (wq >= 1 && lane >= 17) ub[1][pr][m - 32] = u1[pr];
                 }
-                PROF_MARK(4);
-                // The decision rotates over the four quarters; the other three go on to their next frame.
-                if (wq != (int)(n & 3)) { named_bar_arrive(bar_b, 128); continue; }
-                named_bar(bar_b, 128);
-                PROF_MARK(5);
+                const int bar_id = 1 + 2 * set + (int)par;
+                if (p.debug_skip & 16) continue;   // timing experiments: nobody decides
+                if (wq != (int)(n & 3)) { named_bar_arrive(bar_id, 128); continue; }   // (bar.arrive orders the stores above: PTX producer / consumer pattern)
+                named_bar(bar_id, 128);
+                PROF_MARK(3);
                 flush_pending();
                 const unsigned long long f = frame_of(k);
                 const uint32_t *const sl = s.meta[mi];
@@ -433,26 +436,35 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 int b3[3];
 #pragma unroll
                 for (int pr = 0; pr < 3; pr++) {
-                    const int4 e0 = s.part[set][par][pr][0], e1 = s.part[set][par][pr][1], e2 = s.part[set][par][pr][2], e3 = s.part[set][par][pr][3];
-                    // quarters are in ascending lag order: the first one holding the maximum holds the first-max lag; a
-                    // second quarter holding the same value makes the runner-up equal to the maximum (nothing certified)
-                    const int top = max(max(e0.x, e1.x), max(e2.x, e3.x));
-                    const int qa = e0.x == top ? 0 : (e1.x == top ? 1 : (e2.x == top ? 2 : 3));
-                    const int j1 = qa == 0 ? e0.y : (qa == 1 ? e1.y : (qa == 2 ? e2.y : e3.y));
-                    const int second = max(max(qa == 0 ? e0.z : e0.x, qa == 1 ? e1.z : e1.x), max(qa == 2 ? e2.z : e2.x, qa == 3 ? e3.z : e3.x));
+                    // lane holds lag indices j = lane, lane + 32, lane + 64 (ascending): U[j] = n0[j] + n1[j]
+                    int v[3];
+#pragma unroll
+                    for (int t = 0; t < 3; t++) {
+                        const int j = lane + 32 * t;
+                        v[t] = (j >= PAD - L && j <= PAD + L) ? ub[0][pr][j] + ub[1][pr][j] : INT_MIN;
+                    }
+                    // first-max arg-max (correlations.c:20-23 on C9 = 256 U) and the runner-up
+                    const int top_l = max(v[0], max(v[1], v[2]));
+                    const int j_l = v[0] == top_l ? lane : (v[1] == top_l ? lane + 32 : lane + 64);
+                    const int top = __reduce_max_sync(0xffffffffu, top_l);
+                    const int j1 = __reduce_min_sync(0xffffffffu, top_l == top ? j_l : 0x7fffffff);
+                    const int sec_l = max(j1 == lane ? INT_MIN : v[0], max(j1 == lane + 32 ? INT_MIN : v[1], j1 == lane + 64 ? INT_MIN : v[2]));
+                    const int second = __reduce_max_sync(0xffffffffu, sec_l);
                     const int xc = pr == 2 ? 1 : 0, yc = pr == 0 ? 1 : 2;
                     const long long bound = (long long)sqrt_prod_up(sl[xc], sl[yc]) + 1;
                     sure = sure && 256LL * ((long long)top - (long long)second) > 2 * bound && 256LL * top - bound >= 2048;
                     b3[pr] = j1 - PAD;
                 }
+                PROF_MARK(4);
                 if (sure) {
-                    // certified lags are final; the position comes from the peak-tuple table, whose entry is consumed at
-                    // this warp's next turn (flush_pending) so that the load's latency stays off the chain
+                    // certified lags are final; the position comes from the peak-tuple table: the entry is prefetched now and
+                    // read at this warp's next turn (flush_pending), so the load's latency stays off the chain
                     if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? b3[0] : (lane == 1 ? b3[1] : b3[2]);
                     if (lane == 0 && p.gate) p.gate[f] = (b3[0] * b3[0] + b3[1] * b3[1] + b3[2] * b3[2]) > 4 ? 1 : 0;   // sample_compute.h:124-134
                     if (wants_pos) {
-                        pend_e = __ldg(&p.peak_tab[((b3[0] + L) * (2 * L + 1) + (b3[1] + L)) * (2 * L + 1) + (b3[2] + L)]);
-                        pend_f = f; pend = true;
+                        pend_idx = ((b3[0] + L) * (2 * L + 1) + (b3[1] + L)) * (2 * L + 1) + (b3[2] + L);
+                        pend_f = f;
+                        if (lane == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.peak_tab + pend_idx));
                     } else if (lane == 0 && p.stats) atomicAdd(&p.stats[4], 1ull);
                 } else if (lane == 0) {
                     p.redo_list[atomicAdd(p.redo_count, 1u)] = (uint32_t)f;      // the exact variant finishes this frame
@@ -461,6 +473,7 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
             } else {
                 // ---- exact variant: U = 256 hh + mid and ll of the three pairs; corr = 256 U + ll
                 const unsigned long long f = frame_of(k);
+                int (*const spill)[3][32] = s.spill[set][par];
                 long long *const curve = &s.curve[set][0][0];
                 int u0[3], u1[3], l0[3], l1[3];
 #pragma unroll
