@@ -104,6 +104,7 @@ struct UmmaSmem {
     // CERT: diagonal sums of the three pairs by lag index, [set][frame parity][n0 | n1][pair][lag index]; the n1 entries no
     // quarter ever writes stay zero from the kernel's start
     alignas(16) int ubuf[CERT ? G::SETS : 1][2][2][3][128];
+    alignas(16) int4 ptab[4 * G::SETS];                  // CERT: per epilogue warp, the peak-tuple table entry of its last certified frame (cp.async)
     // exact variant
     alignas(16) long long curve[CERT ? 1 : G::SETS][3][G::NJ];   // raw curves by lag index (input of epilogue_warp)
     alignas(16) long long part64[CERT ? 1 : G::SETS][3][4];      // per-warp arg-max keys
@@ -351,13 +352,16 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
         const bool wants_pos = p.cell || p.xy;
         const int bar_a = 1 + 2 * set, bar_b = 2 + 2 * set;      // exact variant
         unsigned par = 0;
-        // CERT: a certified frame whose peak-tuple table entry has been prefetched but not read yet
-        int pend_idx = -1;
+        // CERT: a certified frame whose peak-tuple table entry is on its way into shared memory (cp.async, lane 0); it is
+        // consumed at this warp's next decision, so the table's latency stays off every chain
+        bool pend = false;
         unsigned long long pend_f = 0;
         auto flush_pending = [&]() {
-            if (pend_idx < 0) return;
+            if (!pend) return;
+            pend = false;
             if (lane == 0) {
-                const int4 e = __ldg(&p.peak_tab[pend_idx]);
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                const int4 e = s.ptab[warp];
                 if (e.x >= 0) {
                     if (p.cell) p.cell[pend_f] = e.x;
                     if (p.xy) reinterpret_cast<float2 *>(p.xy)[pend_f] = make_float2(__int_as_float(e.y), __int_as_float(e.z));
@@ -366,7 +370,6 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                     p.redo_list[atomicAdd(p.redo_count, 1u)] = (uint32_t)pend_f;     // lags that are no tuple of the LUT: exact search
                 }
             }
-            pend_idx = -1;
         };
         PROF_DECL;
         unsigned slot = (unsigned)set % G::SLOTS, mi = (unsigned)set % G::META;   // i % SLOTS, i % META, kept incrementally
@@ -450,21 +453,24 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                     const int j1 = __reduce_min_sync(0xffffffffu, top_l == top ? j_l : 0x7fffffff);
                     const int sec_l = max(j1 == lane ? INT_MIN : v[0], max(j1 == lane + 32 ? INT_MIN : v[1], j1 == lane + 64 ? INT_MIN : v[2]));
                     const int second = __reduce_max_sync(0xffffffffu, sec_l);
+                    // |ll| <= B = sqrt(Sl_x Sl_y) (rounded up, < 2^25): the arg-max is certain when 256 (top - second) > 2 B
+                    // and the exact peak 256 top - B >= 2048; both tested a little conservatively in 32-bit arithmetic
                     const int xc = pr == 2 ? 1 : 0, yc = pr == 0 ? 1 : 2;
-                    const long long bound = (long long)sqrt_prod_up(sl[xc], sl[yc]) + 1;
-                    sure = sure && 256LL * ((long long)top - (long long)second) > 2 * bound && 256LL * top - bound >= 2048;
+                    const unsigned bnd = (unsigned)sqrt_prod_up(sl[xc], sl[yc]) + 1u;
+                    sure = sure && (unsigned)(top - second) > (bnd >> 7) + 1u && top > (int)((bnd + 2048u) >> 8) + 1;
                     b3[pr] = j1 - PAD;
                 }
                 PROF_MARK(4);
                 if (sure) {
-                    // certified lags are final; the position comes from the peak-tuple table: the entry is prefetched now and
-                    // read at this warp's next turn (flush_pending), so the load's latency stays off the chain
+                    // certified lags are final; the position comes from the peak-tuple table
                     if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? b3[0] : (lane == 1 ? b3[1] : b3[2]);
                     if (lane == 0 && p.gate) p.gate[f] = (b3[0] * b3[0] + b3[1] * b3[1] + b3[2] * b3[2]) > 4 ? 1 : 0;   // sample_compute.h:124-134
                     if (wants_pos) {
-                        pend_idx = ((b3[0] + L) * (2 * L + 1) + (b3[1] + L)) * (2 * L + 1) + (b3[2] + L);
-                        pend_f = f;
-                        if (lane == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.peak_tab + pend_idx));
+                        if (lane == 0) {
+                            const int idx = ((b3[0] + L) * (2 * L + 1) + (b3[1] + L)) * (2 * L + 1) + (b3[2] + L);
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(&s.ptab[warp])), "l"(p.peak_tab + idx) : "memory");
+                        }
+                        pend_f = f; pend = true;
                     } else if (lane == 0 && p.stats) atomicAdd(&p.stats[4], 1ull);
                 } else if (lane == 0) {
                     p.redo_list[atomicAdd(p.redo_count, 1u)] = (uint32_t)f;      // the exact variant finishes this frame
