@@ -15,8 +15,8 @@ AT_OK, AT_EINVAL, AT_ECUDA, AT_ENOGPU, AT_ENOMEM = 0, -1, -2, -3, -4
 AT_MAX_MICS = 8
 KERNELS = {"auto": 0, "imad": 1, "imma": 2, "umma": 4}
 AT_CORR_PACKED, AT_CORR_STRUCT = 0, 1
-SYNTH_INTEGER_DELAYS, SYNTH_RANDOM_HEADS, SYNTH_KATS = 1, 2, 4
-UBENCH = {"imad_wide": 0, "imad": 1, "dp2a": 2, "dp4a": 3, "imma_s8": 4, "lds": 5, "dfma": 6}
+SYNTH_INTEGER_DELAYS, SYNTH_RANDOM_HEADS, SYNTH_KATS, SYNTH_MAX_NOISE, SYNTH_WHITE = 1, 2, 4, 8, 16
+UBENCH = {"imad_wide": 0, "imad": 1, "dp2a": 2, "dp4a": 3, "imma_s8": 4, "lds": 5, "dfma": 6, "umma_i8": 7, "umma_frame": 8}
 
 
 class AtConfig(C.Structure):

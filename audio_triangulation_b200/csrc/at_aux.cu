@@ -592,6 +592,8 @@ cudaError_t at_run_microbench(int which, int sm_count, double *gops, double *mhz
     case 4: return run_ubench<4>(sm_count, 4.0 * 16 * 8 * 32 / 32.0, gops, mhz, st);  // MAC per lane per iteration
     case 5: return run_ubench<5>(sm_count, 4 * 16, gops, mhz, st);                    // bytes
     case 6: return run_ubench<6>(sm_count, 8, gops, mhz, st);
+    case 7: return at_run_microbench_umma(0, sm_count, gops, mhz, st);                // dense tcgen05 int8 MMAs
+    case 8: return at_run_microbench_umma(1, sm_count, gops, mhz, st);                // G frames/s of a frame's MMA sequence
     default: return cudaErrorInvalidValue;
     }
 }

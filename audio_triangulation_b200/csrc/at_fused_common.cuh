@@ -191,17 +191,17 @@ struct EpiSmem {
 };
 
 // curve[][] holds the raw correlation sums.  All THREADS threads of the group call; it synchronises the group with
-// barrier BAR (BAR = 0 and THREADS = blockDim.x: the whole CTA, i.e. __syncthreads; a warp-specialised kernel passes its
+// barrier bar_id (0 and THREADS = blockDim.x: the whole CTA, i.e. __syncthreads; a warp-specialised kernel passes its
 // own barrier id and the index of the thread within the group).
 template <int NMICS, int NBITS, int L, int THREADS, int BAR = 0>
 __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const float *gauss_s,
-                                         const AtFusedParams &p, unsigned long long f, int tid = threadIdx.x)
+                                         const AtFusedParams &p, unsigned long long f, int tid = threadIdx.x, int bar_id = BAR)
 {
     using G = Geo<NBITS, L>;
     constexpr int P = NMICS * (NMICS - 1) / 2, NL = G::NL, OFF = G::PADL - L; // curve index of lag -L
     constexpr int NWARPS = THREADS / 32;
     const int lane = tid & 31, warp = tid >> 5;
-    auto group_sync = [] { asm volatile("bar.sync %0, %1;" :: "n"(BAR), "n"(THREADS) : "memory"); };
+    auto group_sync = [bar_id] { asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(THREADS) : "memory"); };   // bar_id: group-uniform
 
     // (1) arg-max per pair (correlations.c:20-23): one warp per pair
     for (int pr = warp; pr < P; pr += NWARPS) {

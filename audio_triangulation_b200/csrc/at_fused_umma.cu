@@ -106,7 +106,7 @@ struct UmmaSmem {
     alignas(16) int ubuf[CERT ? G::SETS : 1][2][2][3][128];
     alignas(16) int4 ptab[4 * G::SETS];                  // CERT: per epilogue warp, the peak-tuple table entry of its last certified frame (cp.async)
     // exact variant
-    alignas(16) long long curve[CERT ? 1 : G::SETS][3][G::NJ];   // raw curves by lag index (input of epilogue_warp)
+    alignas(16) EpiSmem<3, 10, L> epi[CERT ? 1 : G::SETS];       // raw curves by lag index + scratch of the group epilogue
     alignas(16) long long part64[CERT ? 1 : G::SETS][3][4];      // per-warp arg-max keys
     alignas(16) int spill[CERT ? 1 : G::SETS][2][6][3][32];      // partial sums that cross a lane quarter: [array][quarter below][lane]
     alignas(16) uint32_t meta[G::META][4];              // per frame: sum of squared low digits of each channel
@@ -116,16 +116,17 @@ struct UmmaSmem {
     uint32_t tmem_base;
 };
 
-// 16 bytes starting sh bytes (1..15) into the 32-byte pair (a, b)
+// 16 bytes starting sh bytes (1..15) into the 32-byte pair (a, b); sh is warp-uniform (one ring head per frame), so the
+// word offset is a branch, not a chain of selects
 __device__ __forceinline__ uint4 realign16(const uint4 a, const uint4 b, int sh)
 {
-    const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     const int ws = sh >> 2, bs = (sh & 3) * 8;
-    uint32_t t[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) t[k] = ws == 0 ? c[k] : (ws == 1 ? c[k + 1] : (ws == 2 ? c[k + 2] : c[k + 3]));
-    return make_uint4(__funnelshift_r(t[0], t[1], bs), __funnelshift_r(t[1], t[2], bs), __funnelshift_r(t[2], t[3], bs),
-                      __funnelshift_r(t[3], t[4], bs));
+    uint32_t t0, t1, t2, t3, t4;
+    if (ws == 0) { t0 = a.x; t1 = a.y; t2 = a.z; t3 = a.w; t4 = b.x; }
+    else if (ws == 1) { t0 = a.y; t1 = a.z; t2 = a.w; t3 = b.x; t4 = b.y; }
+    else if (ws == 2) { t0 = a.z; t1 = a.w; t2 = b.x; t3 = b.y; t4 = b.z; }
+    else { t0 = a.w; t1 = b.x; t2 = b.y; t3 = b.z; t4 = b.w; }
+    return make_uint4(__funnelshift_r(t0, t1, bs), __funnelshift_r(t1, t2, bs), __funnelshift_r(t2, t3, bs), __funnelshift_r(t3, t4, bs));
 }
 
 // 16 ring-ordered ADC bytes of chronological samples [i0, i0 + 16) of one channel (staged in shared memory), any head
@@ -311,10 +312,11 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
 #pragma unroll
                         for (int q = 0; q < 2; q++) prep_chunk(ch, q, raw[ch * 2 + q]);
                 } else {
-#pragma unroll 1
+                    const int uhead = __shfl_sync(0xffffffffu, head, 0);      // tells the compiler what it cannot see: warp-uniform
+#pragma unroll
                     for (int ch = 0; ch < 3; ch++)
 #pragma unroll
-                        for (int q = 0; q < 2; q++) prep_chunk(ch, q, load_chrono16(src + ch * N, q * 512 + lane * 16, head));
+                        for (int q = 0; q < 2; q++) prep_chunk(ch, q, load_chrono16(src + ch * N, q * 512 + lane * 16, uhead));
                 }
             }
             if constexpr (CERT) {
@@ -480,7 +482,8 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 // ---- exact variant: U = 256 hh + mid and ll of the three pairs; corr = 256 U + ll
                 const unsigned long long f = frame_of(k);
                 int (*const spill)[3][32] = s.spill[set][par];
-                long long *const curve = &s.curve[set][0][0];
+                EpiSmem<3, 10, L> &epi = s.epi[set];
+                static_assert(Geo<10, L>::PADL == PAD && Geo<10, L>::NLAGS_PAD == G::NJ, "curve layout of the group epilogue");
                 int u0[3], u1[3], l0[3], l1[3];
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
@@ -505,14 +508,14 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 for (int pr = 0; pr < 3; pr++) {
                     if (wq < 3 && lane >= 17) { u0[pr] += spill[pr][wq][lane]; l0[pr] += spill[3 + pr][wq][lane]; }
                     const long long val = 256LL * (long long)u0[pr] + (long long)l0[pr];
-                    if (m < G::NJ) curve[pr * G::NJ + m] = val;
+                    if (m < G::NJ) epi.curve[pr][m] = val;
                     long long key = valid ? val * 128 + (127 - m) : LLONG_MIN;   // largest value, then lowest lag
                     key = warp_max_i64(key);
                     if (lane == 0) s.part64[set][pr][wq] = key;
                 }
                 named_bar(bar_b, 128);
                 PROF_MARK(4);
-                if (wq == 0) {
+                {   // every thread of the set: the three first-max lags and peaks (correlations.c:20-23)
                     int best3[3];
                     long long peak[3];
 #pragma unroll
@@ -523,12 +526,18 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                         best3[pr] = 127 - (int)(key & 127) - PAD;
                         peak[pr] = key >> 7;
                     }
-                    if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? best3[0] : (lane == 1 ? best3[1] : best3[2]);
+                    if (m < 3 && p.lags) p.lags[f * 3 + m] = m == 0 ? best3[0] : (m == 1 ? best3[1] : best3[2]);
                     const bool extras = p.gate || p.raw || p.corr || p.cell || p.highest || p.xy || p.classes;
                     bool settled = !extras;
+                    // position products only: consistent peaks are settled by one table load (thread 0 of the set stores)
                     if (extras && !(p.raw || p.corr || p.classes))
-                        settled = peak_tuple_lookup<L>(p, f, lane, best3[0], best3[1], best3[2], peak);
-                    if (!settled) epilogue_warp<L, PAD, G::NJ, G::NJ>(curve, best3[0], best3[1], best3[2], s.gauss, p, f, lane);
+                        settled = peak_tuple_lookup<L>(p, f, m, best3[0], best3[1], best3[2], peak);
+                    // everything else -- whole curves, flat or inconsistent curves -- by the whole set: Gaussian re-weighting,
+                    // result stores and the likelihood maximum over all LUT tuples with 128 threads
+                    if (!settled) {
+                        if (m == 0 && p.stats && (p.cell || p.highest || p.xy || p.classes)) atomicAdd(&p.stats[2], 1ull);   // route: full scan
+                        epilogue<3, 10, L, 128>(epi, s.gauss, p, f, m, bar_a);
+                    }
                 }
                 named_bar(bar_a, 128);      // curve / part64 are rewritten by the next frame of this set
                 PROF_MARK(6);
@@ -587,4 +596,94 @@ cudaError_t at_launch_fused_umma(const AtShape &sh, const AtFusedParams &p_in, u
     // the frames the certified pass could not settle: exact variant over the list (length read on the device)
     p.frame_list = redo + 1; p.list_count = redo; p.redo_count = nullptr; p.redo_list = nullptr;
     return sh.max_shift == 46 ? launch_umma<46, false>(p, p.n_frames, sm_count, st) : launch_umma<44, false>(p, p.n_frames, sm_count, st);
+}
+
+// ------------------------------------------------------------------ roofline denominators, measured live (at_microbench)
+namespace atk {
+// which = 0: dense tcgen05.mma kind::i8 M128 x N256 x K32 back to back (the tensor core's int8 rate);
+// which = 1: the eight MMAs of a frame of the certified variant (Hankel A, N = 64 / 32 / 32 / 16 per K-step) from rotating
+//            plane buffers: what this formulation can draw from the tensor core when nothing else runs.
+__global__ void __launch_bounds__(128) umma_ubench_kernel(int which, int reps, long long *cycles)
+{
+    constexpr int PLANE = 1152, FRAMEB = 6 * PLANE, NBUF = 7, PAD = 48;
+    extern __shared__ __align__(128) uint8_t dyn[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < NBUF * FRAMEB / 4; i += 128) reinterpret_cast<uint32_t *>(dyn)[i] = (uint32_t)i * 2654435761u;
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+    const long long t0 = clock64();
+    if (warp == 0) {
+        if (elect_one()) {
+            constexpr uint32_t LBO = (128u >> 4) << 16, HI_A = (16u >> 4) | 0x4000u;
+            constexpr uint32_t HI_B1 = ((uint32_t)PLANE >> 4) | 0x4000u, HI_B2 = ((uint32_t)(2 * PLANE) >> 4) | 0x4000u;
+            constexpr uint32_t I256 = umma_idesc(256), I64 = umma_idesc(64), I32 = umma_idesc(32), I16 = umma_idesc(16);
+            for (int r = 0; r < reps; r++) {
+                const uint32_t b16 = (smem_u32(dyn + (r % NBUF) * FRAMEB) >> 4) + LBO;
+                const uint32_t cb = tmem + (uint32_t)(r & 3) * 128;
+                auto hk = [&](int pl, int kk) { return b16 + (uint32_t)((pl * PLANE + 512 * kk) >> 4); };
+                auto xs = [&](int pl, int kk) { return b16 + (uint32_t)((pl * PLANE + PAD + 512 * kk) >> 4); };
+                if (which == 0) {
+                    // B: 16 "planes" of 16 phases, 128 bytes apart (any readable bytes will do for a rate measurement)
+                    umma_i8_lohi(tmem + (uint32_t)(r & 1) * 256, hk(0, r & 1), HI_A, xs(1, 0), (128u >> 4) | 0x4000u, I256, 1);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 2; kk++) {
+                        umma_i8_lohi(cb + 0, hk(4, kk), HI_A, xs(0, kk), HI_B1, I64, kk);
+                        umma_i8_lohi(cb + 32, hk(5, kk), HI_A, xs(0, kk), HI_B1, I32, 1);
+                        umma_i8_lohi(cb + 64, hk(1, kk), HI_A, xs(0, kk), HI_B2, I32, kk);
+                        umma_i8_lohi(cb + 80, hk(3, kk), HI_A, xs(0, kk), HI_B2, I16, 1);
+                    }
+                }
+            }
+            umma_commit(&bar);
+        }
+        __syncwarp();
+        mbar_wait(&bar, 0);
+    }
+    const long long t1 = clock64();
+    if (tid == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+}
+} // namespace atk
+
+// which = 0: *gops = G int8-MAC/s of dense tcgen05 MMAs; which = 1: *gops = G frames/s of the certified variant's MMA sequence
+cudaError_t at_run_microbench_umma(int which, int sm_count, double *gops, double *mhz, cudaStream_t st)
+{
+    long long *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(long long));
+    if (e != cudaSuccess) return e;
+    const int smem = 7 * 6 * 1152, reps = which == 0 ? 20000 : 4000;
+    e = cudaFuncSetAttribute(atk::umma_ubench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { cudaFree(d); return e; }
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    atk::umma_ubench_kernel<<<sm_count, 128, smem, st>>>(which, 64, d);          // warm-up
+    cudaEventRecord(ev0, st);
+    atk::umma_ubench_kernel<<<sm_count, 128, smem, st>>>(which, reps, d);
+    cudaEventRecord(ev1, st);
+    at_count_launch(2);
+    e = cudaEventSynchronize(ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    long long cyc = 0;
+    cudaMemcpy(&cyc, d, sizeof cyc, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (e != cudaSuccess) return e;
+    const double per_rep = which == 0 ? 128.0 * 256.0 * 32.0 : 1.0;
+    *gops = per_rep * reps * sm_count / (ms * 1e-3) / 1e9;
+    if (mhz) *mhz = (double)cyc / (ms * 1e-3) / 1e6;
+    return cudaGetLastError();
 }

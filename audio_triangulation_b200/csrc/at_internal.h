@@ -62,6 +62,7 @@ bool at_fused_imma_cta_supports(const AtShape &shape);
 // redo: device scratch of 4 * (n_frames + 1) bytes whose first word is zero (certified pass + exact pass over its list), or NULL
 cudaError_t at_launch_fused_umma(const AtShape &shape, const AtFusedParams &p, uint32_t *redo, int sm_count, cudaStream_t st);
 bool at_fused_umma_window_ok(const int16_t *window, int n);
+cudaError_t at_run_microbench_umma(int which, int sm_count, double *gops, double *mhz, cudaStream_t st);
 bool at_fused_umma_supports(const AtShape &shape);
 // at_fused_umma_m.cu -- tcgen05 (UMMA) kernel for 8-microphone arrays, 1024 / 4096 samples
 cudaError_t at_launch_fused_umma_m(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);

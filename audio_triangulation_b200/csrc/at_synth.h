@@ -22,6 +22,9 @@
 #define AT_SYNTH_F_INTEGER_DELAYS 1u
 #define AT_SYNTH_F_RANDOM_HEADS 2u
 #define AT_SYNTH_F_KATS 4u
+#define AT_SYNTH_F_MAX_NOISE 8u    /* every frame at the lowest SNR of the model (noise scale 6) */
+#define AT_SYNTH_F_WHITE 16u       /* no source at all: independent uniform bytes (worst case for every shortcut) */
+#define AT_SYNTH_KAT_WHITE 100
 #define AT_SYNTH_N_KATS 4
 
 AT_HD uint64_t at_mix64(uint64_t z)
@@ -61,8 +64,8 @@ AT_HD at_synth_frame at_synth_frame_params(uint64_t seed, uint32_t flags, uint64
     p.cell = (int32_t)((h & 0xFFFFFFull) % (uint64_t)n_cells);
     p.head = (flags & AT_SYNTH_F_RANDOM_HEADS) ? (int32_t)((h >> 24) & ((1u << n_bits) - 1)) : 0;
     const uint32_t sel = (uint32_t)((h >> 40) % 3u);
-    p.noise_mul = sel == 0 ? 0 : (sel == 1 ? 2 : 6);
-    p.kat = ((flags & AT_SYNTH_F_KATS) && f < AT_SYNTH_N_KATS) ? (int32_t)f : -1;
+    p.noise_mul = (flags & AT_SYNTH_F_MAX_NOISE) ? 6 : (sel == 0 ? 0 : (sel == 1 ? 2 : 6));
+    p.kat = ((flags & AT_SYNTH_F_KATS) && f < AT_SYNTH_N_KATS) ? (int32_t)f : ((flags & AT_SYNTH_F_WHITE) ? AT_SYNTH_KAT_WHITE : -1);
     return p;
 }
 
@@ -87,6 +90,7 @@ AT_HD int32_t at_synth_kat(int kat, int mic, int i)
 AT_HD uint8_t at_synth_sample(uint64_t seed, uint64_t f, const at_synth_frame &p, int mic, int i,
                               int32_t delay_q8)
 {
+    if (p.kat == AT_SYNTH_KAT_WHITE) return (uint8_t)(at_hash_final(at_hash_prefix(seed, f, 2 + (uint64_t)mic), (uint64_t)i) & 0xFF);
     if (p.kat >= 0) return (uint8_t)at_synth_kat(p.kat, mic, i);
     const uint64_t hm = at_hash3(seed, f, 0xDCull, (uint64_t)mic);
     const int32_t dc = (int32_t)(hm % 17u) - 8;

@@ -7,8 +7,9 @@
 Workload (N=1): BASELINE.json configs[1] -- 2^20 synthetic frames, reference geometry (3 mics x
 1024 samples, +-46 lags, 50 kHz), fixed-point direct cross-correlation, outputs = 3 TDOA lags +
 likelihood-map cell + plane coordinates per frame.  N>1: every rank holds its own 2^20-frame
-slice of a batch N times larger (weak scaling, contiguous frame ranges, no data-path collective)
-and the per-frame results are gathered to rank 0 over NCCL inside the timed region.
+slice of a batch N times larger (weak scaling, contiguous frame ranges, no data-path collective);
+every rank's kernel stores its 24 B/frame of results straight into rank 0's result arrays
+(CUDA-IPC mapped peer memory: the only bytes that cross NVLink), inside the timed region.
 A step = one pass of the hot path over the whole batch.  The input (3.2 GB per GPU) is far larger
 than L2 (126 MB), so no explicit L2 flush is needed between timed iterations.
 Prints ONE JSON line on rank 0.
@@ -30,32 +31,9 @@ BYTES_IN_PER_FRAME = 3 * 1024   # uint8 ADC bytes
 FRAMES_DEFAULT = 1 << 20
 WANT = ("lags", "cell", "xy")
 BYTES_OUT_PER_FRAME = 3 * 4 + 4 + 8
-
-
-def bind_to_gpu_numa_node(index):
-    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the
-    end-to-end leg are allocated next to the GPU's PCIe root (matters from 4 ranks up).  Best effort; returns the node."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
-        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
-        if len(bus.split(":")[0]) > 4:
-            bus = bus[-12:]                                   # nvml reports an 8-digit PCI domain, sysfs uses 4
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return node
-    except Exception:
-        pass
-    return None
+SYNTH_KATS, SYNTH_RANDOM_HEADS, SYNTH_MAX_NOISE, SYNTH_WHITE = 4, 2, 8, 16
+WORKLOAD = ("BASELINE configs[1]: 2^20 synthetic frames per GPU, reference geometry (3 mics x 1024 samples, "
+            "+-46 lags, 50 kHz), fixed-point direct xcorr, outputs lags+cell+xy")
 
 
 def dist_env():
@@ -101,12 +79,13 @@ class ClockSampler(threading.Thread):
 
 # --------------------------------------------------------------------------- reference arm / cpu baseline
 def reference_lib():
+    """The CPU checker: the reference's own objects (oracle/_ref) when they were built, else the restated oracle.
+    Never touches the product library."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_bindings import Oracle, load_ref
     ref = load_ref(fast=True)
-    if ref is not None:
-        return "reference", ref, None
-    return "port", None, Oracle()
+    port = Oracle()
+    return ("reference" if ref is not None else "port"), ref, port
 
 
 def reference_run(kind, ref, port, adc, nthreads):
@@ -120,64 +99,62 @@ def reference_run(kind, ref, port, adc, nthreads):
     return time.perf_counter() - t0, lags
 
 
-def sample_frames(n):
-    """Frames of the bench workload for the CPU legs: the product's generator when a GPU is there
-    (identical bytes to the GPU arm), numpy bursts otherwise."""
-    try:
-        import torch
-        if torch.cuda.is_available():
-            import audio_triangulation_b200 as at
-            loc = at.Localizer(device=0)
-            adc, _, _ = loc.synth_device(n, flags=4)
-            torch.cuda.synchronize()
-            out = adc.cpu().numpy()
-            loc.close()
-            return out, "at_synth_device frames [0,%d) of the bench batch" % n
-    except Exception:
-        pass
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from frames import burst_frames
-    return burst_frames(n, seed=1)[0], "numpy burst frames (no GPU for the product generator)"
-
-
 def run_reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
     kind, ref, port = reference_lib()
     cores = os.cpu_count() or 1
-    # size one step to roughly 2 s of all-core work
-    probe, how = sample_frames(2048)
-    dt, _ = reference_run(kind, ref, port, probe, cores)
-    per_step = int(max(2048, min(1 << 18, 2.0 * 2048 / max(dt, 1e-6))))
-    adc, how = sample_frames(per_step)
-    for _ in range(args.warmup):
+    F = args.frames
+    # The same batch as our arm -- frames [0, F) of the generator -- built on the host by oracle/synth_host.cpp
+    # (the generator header, compiled into the checker), so this arm maps nothing but oracle/ and oracle/_ref.
+    t0 = time.perf_counter()
+    adc, _, _ = port.synth(F, flags=SYNTH_KATS, first_frame=0, nthreads=cores)
+    gen_s = time.perf_counter() - t0
+    for _ in range(min(args.warmup, 1)):      # one untimed pass warms the page cache / thread pool; more buys nothing on a CPU
         reference_run(kind, ref, port, adc, cores)
     t = 0.0
     for _ in range(args.steps):
         dt, _ = reference_run(kind, ref, port, adc, cores)
         t += dt
-    value = per_step * args.steps / t
+    value = F * args.steps / t
     line = {"impl": "reference", "metric": "localized frames/sec", "value": value, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16 x int16 -> int64",
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: reference geometry 3 mics x 1024 samples, +-46 lags; "
-                                   "bounded sample of %d frames per step" % per_step, "frames_per_step": per_step},
+            "config": {"workload": WORKLOAD, "frames_per_gpu": F, "global_frames": F,
+                       "note": "the reference's own sample_compute steps (write_out, <<8, window, 3 x correlations_init) on "
+                               "all host threads; one step = the whole 2^20-frame batch"},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
-                             "sample": "%d frames/step, %s; reference objects -O3 x86-64-v3, one pthread per core" % (per_step, how)},
+                             "sample": "frames [0, %d) of the bench batch per step (generated on the host in %.1f s by "
+                                       "oracle/synth_host.cpp); reference objects -O3 x86-64-v3, one pthread per core"
+                                       % (F, gen_s)},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
+def time_device(loc, torch, stream, adc, heads, want, steps, out=None, struct_corr=False):
+    """Device-resident throughput of one output selection: frames/s over `steps` launches (3 warm-up launches)."""
+    out = {} if out is None else out
+    for _ in range(3):
+        loc.localize_device(adc, heads, want=want, out=out, struct_corr=struct_corr)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+        loc.localize_device(adc, heads, want=want, out=out, struct_corr=struct_corr)
+    b.record(stream)
+    torch.cuda.synchronize()
+    return adc.shape[0] * steps / (a.elapsed_time(b) * 1e-3)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import audio_triangulation_b200 as at
 
     rank, local_rank, world = dist_env()
-    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -190,60 +167,74 @@ def run_ours(args):
     from audio_triangulation_b200.sharding import frame_range
     lo, hi = frame_range(rank, world, world * F)
     assert hi - lo == F
-    adc, _, _ = loc.synth_device(F, flags=4 if rank == 0 else 0, first_frame=lo)
-    outs = [{}, {}]            # double-buffered results: the gather of step i overlaps the kernel of step i+1
-    out = outs[0]
-    gathered = None
-    comm = torch.cuda.Stream(dev) if world > 1 else None
-    if world > 1 and rank == 0:
-        gathered = [torch.empty((F, 3), dtype=torch.int32, device=dev) for _ in range(world)]
+    adc, _, _ = loc.synth_device(F, flags=SYNTH_KATS if rank == 0 else 0, first_frame=lo)
 
-    def step(i):
-        o = outs[i & 1]
-        loc.localize_device(adc, None, want=WANT, out=o)
-        if world > 1:   # the only bytes that cross NVLink: 12 B of lags per frame to rank 0, on a side stream
-            ready = torch.cuda.Event()
-            ready.record(stream)
-            comm.wait_event(ready)
-            with torch.cuda.stream(comm):
-                dist.gather(o["lags"], gathered, dst=0)
+    # Result arrays.  N > 1: rank 0 owns arrays for the GLOBAL batch and every rank maps them (CUDA IPC); each rank's
+    # kernel stores its slice there directly, so the "gather" is the epilogue's own 24 B/frame of stores over NVLink.
+    shapes = {"lags": ((F, 3), torch.int32), "cell": ((F,), torch.int32), "xy": ((F, 2), torch.float32)}
+    glob = None
+    if world > 1:
+        from torch.multiprocessing.reductions import reduce_tensor
+        handles = [None]
+        if rank == 0:
+            glob = {k: torch.zeros((world,) + s, dtype=d, device=dev) for k, (s, d) in shapes.items()}
+            handles = [{k: reduce_tensor(v) for k, v in glob.items()}]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            glob = {k: fn(*a) for k, (fn, a) in handles[0].items()}     # rank 0's memory, mapped here
+        out = {k: v[rank] for k, v in glob.items()}
+    else:
+        out = {k: torch.empty(s, dtype=d, device=dev) for k, (s, d) in shapes.items()}
+
+    def step():
+        loc.localize_device(adc, None, want=WANT, out=out)
 
     def barrier():
-        if comm is not None:
-            stream.wait_stream(comm)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
+    for _ in range(max(args.warmup, 3)):
+        step()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = loc.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0.record(stream)
-    for i in range(args.steps):
-        kev[i][0].record(stream)
-        step(i)
-        kev[i][1].record(stream)          # main stream: brackets the localization kernel only
-    if comm is not None:
-        stream.wait_stream(comm)          # the last gather is inside the timed region
+    for _ in range(args.steps):
+        step()
     ev1.record(stream)
     barrier()
     launches = loc.kernel_launches() - launches0
     clocks = sampler.finish()
     total_ms = ev0.elapsed_time(ev1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms = t.tolist()
+    total_ms = t.item()
+    kern_ms = total_ms / args.steps          # the step IS the kernel (certified pass + exact pass over its short list)
     value = world * F * args.steps / (total_ms * 1e-3)
 
-    # ---- how the (exact) bounded likelihood search resolved the frames of this batch (untimed extra pass)
+    # ---- (untimed) are the sharded results byte-identical to a single-GPU computation of the same frame ranges?
+    sharded_ok = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            sharded_ok = True
+            chk = {}
+            for r in range(world):
+                rlo, _ = frame_range(r, world, world * F)
+                radc, _, _ = loc.synth_device(F, flags=SYNTH_KATS if r == 0 else 0, first_frame=rlo)
+                loc.localize_device(radc, None, want=WANT, out=chk)
+                torch.cuda.synchronize(dev)
+                for k in WANT:
+                    sharded_ok = sharded_ok and bool(torch.equal(chk[k].view(torch.uint8), glob[k][r].view(torch.uint8)))
+                del radc
+        barrier()
+
+    # ---- how the frames of this batch were settled (untimed extra pass)
     search = None
     try:
         st = loc.localize_device(adc, None, want=WANT + ("stats",))["stats"]
@@ -275,77 +266,103 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * F * e2e_steps / te.item()
-    e2e_ok = bool((hout["lags"].numpy() == out["lags"].cpu().numpy()).all())
-
-    # ---- roofline of the dominant (only) kernel
-    kernel_used = args.kernel
-    ubench = {}
-    if rank == 0:
-        for name in ("imma_s8", "imad_wide", "imad", "dp2a", "lds"):
-            try:
-                g, mhz = loc.microbench(name)
-                ubench[name] = {"gops": g}
-            except Exception as e:   # pragma: no cover
-                ubench[name] = {"error": str(e)}
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_ach = (BYTES_IN_PER_FRAME + BYTES_OUT_PER_FRAME) * F / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_frame") * F
-    except Exception:
-        pass
+    e2e_ok = all(bool((hout[k].numpy() == out[k].cpu().numpy()).all()) for k in WANT)
+    h2d_gbs = world * F * BYTES_IN_PER_FRAME * e2e_steps / te.item() / 1e9
+    del pinned
 
     line = None
     if rank == 0:
-        # The auto / imma kernel computes the 279,210 int16 MACs of a frame as 4 x 279,210 int8 MACs on the
-        # tensor cores (byte-split Toeplitz x Hankel tiles); padded to whole 16x8x32 tiles that is 396 IMMA =
-        # 1,622,016 int8 MACs -- of which the l.l digit product (99 IMMA) is issued only for the frames whose
-        # arg-max the other nine products cannot certify.  Peak = legacy mma.sync int8 rate measured live on this GPU
-        # (MEASURED_PEAKS.json carries no int8 figure; its bf16 number is the tcgen05 path this kernel cannot use,
-        # see DESIGN.md).  The imad kernel is measured against the IMAD.WIDE chain rate instead.
-        imma = kernel_used in ("auto", "imma", "imma_lm")
-        peak_name = "imma_s8" if imma else "imad_wide"
-        peak = ubench.get(peak_name, {}).get("gops", 0.0) / 1e3
-        per_frame = MAC_PER_FRAME * (4 if imma else 1)
-        certified = (search or {}).get("lags_certified_without_ll_product", 0.0) if kernel_used in ("auto", "imma") else 0.0
-        issued_per_frame = 4096 * 33 * (9 + 3 * (1.0 - certified))          # int8 MACs on the tensor pipe per frame
+        # ---- the whole truth about the path (N = 1): other output selections, other inputs (fewer steps each)
+        extra = {}
+        if world == 1 and not args.no_extras:
+            k = max(2, min(args.steps, args.extra_steps))
+            modes = {"lags_cell_xy": value,
+                     "lags_only": time_device(loc, torch, stream, adc, None, ("lags",), k)}
+            Fc = min(F, 1 << 18)     # whole correlations_t structs: 2 280 B/frame of output
+            modes["full_corr_struct"] = time_device(loc, torch, stream, adc[:Fc], None, ("lags", "corr"), k, struct_corr=True)
+            modes["full_corr_struct_frames"] = Fc
+            extra["modes"] = modes
+            worst = {}
+            for name, flags in (("white_noise", SYNTH_WHITE), ("lowest_snr", SYNTH_MAX_NOISE)):
+                wloc = at.Localizer(device=local_rank, kernel=args.kernel)    # its own context: its own launch history
+                wadc, _, _ = wloc.synth_device(F, flags=flags, first_frame=0)
+                torch.cuda.synchronize(dev)
+                worst[name] = time_device(wloc, torch, stream, wadc, None, WANT, k)
+                st = wloc.localize_device(wadc, None, want=WANT + ("stats",))["stats"].cpu().numpy().astype(float)
+                worst[name + "_certified_frac"] = float(st[4] / F)
+                del wadc
+                wloc.close()
+            extra["worst_case"] = worst
+            hadc, hheads, _ = loc.synth_device(F, flags=SYNTH_KATS | SYNTH_RANDOM_HEADS, first_frame=0)
+            torch.cuda.synchronize(dev)
+            extra["random_ring_heads"] = time_device(loc, torch, stream, hadc, hheads, WANT, k)
+            del hadc, hheads
+            extra["certified_frac"] = (search or {}).get("lags_certified_without_ll_product")
+
+        # ---- roofline of the dominant kernel
+        ubench = {}
+        for name in ("umma_i8", "umma_frame", "imma_s8", "imad_wide", "imad", "lds"):
+            try:
+                g, _ = loc.microbench(name)
+                ubench[name] = g
+            except Exception as e:   # pragma: no cover
+                ubench[name] = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_ach = (BYTES_IN_PER_FRAME + BYTES_OUT_PER_FRAME) * F / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_frame") * F
+        except Exception:
+            pass
+        tc = args.kernel in ("auto", "umma")
+        # auto / umma: the 279 210 int16 MACs of a frame are 4 x 279 210 int8 MACs on the tcgen05 tensor cores (polyphase
+        # Hankel MMAs); peak = dense tcgen05 kind::i8 rate measured live on this GPU (MEASURED_PEAKS.json has no int8
+        # figure).  imma: legacy mma.sync int8 rate; imad: IMAD.WIDE chain rate.
+        peak_name = "umma_i8" if tc else ("imma_s8" if args.kernel == "imma" else "imad_wide")
+        peak = (ubench.get(peak_name) or 0.0) / 1e3
+        per_frame = MAC_PER_FRAME * (1 if args.kernel == "imad" else 4)
         achieved = per_frame * F / (kern_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor" if imma else "int-pipe",
+        certified = (search or {}).get("lags_certified_without_ll_product") or 0.0
+        # MACs put on the tensor core per frame: the certified pass issues N = 64 + 32 + 32 + 16 columns per K-step (two
+        # K-steps, M = 128, K = 32); the frames it cannot settle get the exact pass (N = 192 per K-step) on top
+        issued = 2 * 144 * 128 * 32 + (1.0 - certified) * 2 * 192 * 128 * 32
+        seq = ubench.get("umma_frame")
+        roof = {"bound": "tensor" if args.kernel != "imad" else "int-pipe",
                 "achieved": achieved, "peak": peak,
-                "unit": "T int8-MAC/s (4 per int16 MAC, useful lags only)" if imma else "T int16-MAC/s",
+                "unit": "T int8-MAC/s (4 per int16 MAC, useful lags only)" if args.kernel != "imad" else "T int16-MAC/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
                 "peak_source": "measured live: at_microbench(%s) on this GPU" % peak_name,
-                "issued_frac": (achieved * issued_per_frame / per_frame / peak) if (imma and peak) else None,
-                "issued_int8_mac_per_frame": issued_per_frame if imma else None,
-                # the same work expressed against the INTEGER-pipe roofline the direct form would have:
-                # 279,210 int16 MAC per frame vs the measured one-instruction-per-MAC rates of this GPU
+                # what the formulation can draw from the tensor core: a frame is eight M128 x N<=64 x K32 MMAs whose
+                # Hankel A operand (4 KB each, re-fetched from shared memory per MMA) bounds them, not the MAC array
+                "tensor_sequence_frames_per_s": seq * 1e9 if seq else None,
+                "frac_of_tensor_sequence": (F / (kern_ms * 1e-3)) / (seq * 1e9) if seq else None,
+                "issued_int8_mac_per_frame": issued if tc else None,
                 "int16_tmac_per_s": MAC_PER_FRAME * F / (kern_ms * 1e-3) / 1e12,
-                "vs_int_pipe_roofline": {
-                    "imad_32bit_peak": (MAC_PER_FRAME * F / (kern_ms * 1e-3) / 1e9) / ubench["imad"]["gops"] if ubench.get("imad", {}).get("gops") else None,
-                    "mad_wide_chain_peak": (MAC_PER_FRAME * F / (kern_ms * 1e-3) / 1e9) / ubench["imad_wide"]["gops"] if ubench.get("imad_wide", {}).get("gops") else None},
                 "kernel_ms": kern_ms, "algorithmic_mac_per_frame": MAC_PER_FRAME,
                 "hbm_achieved_gbs": hbm_ach, "hbm_peak_gbs": hbm_peak, "hbm_frac": hbm_ach / hbm_peak,
                 "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
-                "microbench_gops": {k: v.get("gops") for k, v in ubench.items()}}
+                "microbench_gops": ubench}
         line = {"metric": "localized frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int16 x int16 -> int64, computed as 4 x (int8 x int8 -> int32) on tensor cores (u8 ADC in)", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: 2^20 synthetic frames per GPU, reference geometry "
-                                       "(3 mics x 1024 samples, +-46 lags, 50 kHz), fixed-point direct xcorr, "
-                                       "outputs lags+cell+xy", "frames_per_gpu": F, "global_frames": world * F,
-                           "kernel": kernel_used, "likelihood_search": search, "l2": "inputs (3.2 GB/GPU) larger than L2, no flush",
-                           "sharding": "contiguous frame ranges, lags gathered to rank 0 over NCCL" if world > 1 else "single GPU"},
+                "config": {"workload": WORKLOAD, "frames_per_gpu": F, "global_frames": world * F,
+                           "kernel": args.kernel, "likelihood_search": search, "l2": "inputs (3.2 GB/GPU) larger than L2, no flush",
+                           "sharding": ("contiguous frame ranges; every rank's kernel stores its 24 B/frame straight into rank 0's "
+                                        "arrays (CUDA-IPC peer memory over NVLink)") if world > 1 else "single GPU"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * BYTES_IN_PER_FRAME,
                         "d2h_bytes_per_step": F * BYTES_OUT_PER_FRAME, "steps": e2e_steps, "matches_device_path": e2e_ok,
-                        "rank0_numa_node": numa_node},
+                        "aggregate_h2d_gbs": h2d_gbs},
                 "roofline": roof}
+        if world > 1:
+            line["sharded_bytes_identical"] = sharded_ok
+        line.update(extra)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own objects on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -366,6 +383,7 @@ def run_ours(args):
         emit(line)
     if world > 1:
         dist.barrier()
+        del out, glob
         dist.destroy_process_group()
 
 
@@ -396,8 +414,10 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES_DEFAULT, help="frames per GPU per step")
     ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "imma", "umma"])
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--extra-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

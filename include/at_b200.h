@@ -247,6 +247,8 @@ int at_stream_push(at_stream *s, const uint8_t *d_samples /*[A][ticks][mics]*/, 
 #define AT_SYNTH_INTEGER_DELAYS 1u  /* round per-mic delays to whole samples */
 #define AT_SYNTH_RANDOM_HEADS 2u    /* store frames rotated by a random ring head */
 #define AT_SYNTH_KATS 4u            /* frames 0..3 of the sequence are the known-answer frames */
+#define AT_SYNTH_MAX_NOISE 8u       /* every frame at the model's lowest signal-to-noise ratio */
+#define AT_SYNTH_WHITE 16u          /* no source: independent uniform bytes per channel (worst case of every data-dependent shortcut) */
 int at_synth_host(const at_context *ctx, uint64_t seed, uint32_t flags, size_t first_frame, size_t n_frames,
                   uint8_t *adc, int32_t *heads, int32_t *true_cell);
 int at_synth_device(at_context *ctx, uint64_t seed, uint32_t flags, size_t first_frame, size_t n_frames,
@@ -262,6 +264,8 @@ int at_synth_device(at_context *ctx, uint64_t seed, uint32_t flags, size_t first
 #define AT_UBENCH_IMMA_S8 4
 #define AT_UBENCH_LDS 5
 #define AT_UBENCH_DFMA 6
+#define AT_UBENCH_UMMA_I8 7     /* dense tcgen05.mma kind::i8 M128 x N256 x K32: *gops = G int8-MAC/s */
+#define AT_UBENCH_UMMA_FRAME 8  /* the eight Hankel MMAs of one reference-shape frame, back to back: *gops = G frames/s */
 int at_microbench(at_context *ctx, int which, double *gops, double *sm_mhz_est);
 
 #ifdef __cplusplus

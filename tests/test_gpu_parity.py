@@ -395,7 +395,8 @@ def test_edge_cases(loc):
         at.Localizer(device=0, max_shift=200)
     before = loc.kernel_launches()
     loc.localize_device(one, want=("lags",))
-    assert loc.kernel_launches() == before + 1
+    # one fused launch per call -- two for the tcgen05 kernel of the reference shape (certified pass + exact pass over its list)
+    assert loc.kernel_launches() - before in (1, 2)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -412,10 +413,13 @@ def test_ragged_small_batches(kernel, oracle):
         assert (r["cell"].cpu().numpy() == o["cell"][:F]).all() and (r["highest"].cpu().numpy() == o["highest"][:F]).all(), F
 
 
-def test_bounded_search_paths_are_exercised(loc, oracle):
-    """The likelihood search must take its routes (peak-tuple look-up / first box / widened box / full scan) on suitable data and
-    still equal the oracle's full scan: clean bursts, heavy-noise frames, and flat frames."""
+@pytest.mark.parametrize("kernel", ("auto", "imma"))
+def test_bounded_search_paths_are_exercised(kernel, oracle):
+    """The likelihood search must take its routes on suitable data and still equal the oracle's full scan: clean bursts,
+    heavy-noise frames, and flat frames.  Routes: peak-tuple look-up / full scan over all LUT tuples for the tcgen05 kernel
+    (AUTO), plus the first and the widened box of the warp-scope bounded search for the mma.sync kernel."""
     torch = _torch()
+    loc = make_loc(kernel)
     rng = np.random.default_rng(17)
     clean, _ = burst_frames(256, seed=3)
     noisy = rng.integers(0, 256, (256, 3, N), dtype=np.uint8)                      # white noise: inconsistent peaks
@@ -429,7 +433,9 @@ def test_bounded_search_paths_are_exercised(loc, oracle):
     o = oracle.localize(adc, want_corr=False, nthreads=8)
     assert (r["cell"].cpu().numpy() == o["cell"]).all() and (r["highest"].cpu().numpy() == o["highest"]).all()
     st = r["stats"].cpu().numpy()
-    assert st[:4].sum() == adc.shape[0] and st[3] > 0 and st[2] > 0 and st[0] + st[1] > 0, st   # look-up, a bounded box and the full scan all used
+    assert st[:4].sum() == adc.shape[0] and st[3] > 0 and st[2] > 0, st          # look-up and full scan used
+    if kernel == "imma":
+        assert st[0] + st[1] > 0, st                                              # and a bounded box
     # without `highest` the tensor kernel may certify the arg-max from nine of the twelve digit products (no l.l):
     # same lags and cells, and the clean bursts must take that route while white noise and flat frames must not
     r2 = loc.localize_device(d, want=("lags", "cell", "stats"))
