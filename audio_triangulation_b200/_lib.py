@@ -68,6 +68,10 @@ def load():
         "at_shape": (C.c_int, [ctx] + [C.POINTER(i32)] * 5),
         "at_localize_device": (C.c_int, [ctx, vp, vp, sz, C.POINTER(AtOutputs), vp]),
         "at_localize_host": (C.c_int, [ctx, vp, vp, sz, C.POINTER(AtOutputs)]),
+        "at_peer_enable": (C.c_int, [ctx, i32]),
+        "at_shared_alloc": (C.c_int, [ctx, sz, C.POINTER(vp), C.c_char_p]),
+        "at_shared_open": (C.c_int, [ctx, C.c_char_p, C.POINTER(vp)]),
+        "at_shared_close": (C.c_int, [ctx, vp, i32]),
         "at_localize_host_sharded": (C.c_int, [C.POINTER(ctx), C.c_int, vp, vp, sz, C.POINTER(AtOutputs)]),
         "at_synchronize": (C.c_int, [ctx]),
         "at_average_device": (C.c_int, [ctx, vp, vp, vp, vp, vp, sz, u64, vp]),

@@ -23,6 +23,39 @@ def _np_ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+class DevPtr:
+    """A raw device pointer where the API takes a tensor (only .data_ptr() is used)."""
+
+    def __init__(self, ptr):
+        self.ptr = int(ptr)
+
+    def data_ptr(self):
+        return self.ptr
+
+
+class SharedArray:
+    """Result memory that lives on one GPU and is mapped by the processes driving the others (Localizer.shared_alloc /
+    shared_open).  .view(offset, nbytes) gives a DevPtr to pass as an output of localize_device; on the owning process
+    .tensor() exposes the bytes to torch (zero copy, __cuda_array_interface__)."""
+
+    def __init__(self, loc, ptr, nbytes, handle, opened):
+        self.loc, self.ptr, self.nbytes, self.handle, self.opened = loc, ptr, nbytes, handle, opened
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    def view(self, offset, nbytes):
+        assert 0 <= offset and offset + nbytes <= self.nbytes
+        return DevPtr(self.ptr + offset)
+
+    def tensor(self):
+        import torch
+        return torch.as_tensor(self, device="cuda:%d" % self.loc.device)
+
+    def close(self):
+        if self.ptr:
+            L.check(self.loc.lib.at_shared_close(self.loc.ctx, C.c_void_p(self.ptr), 1 if self.opened else 0))
+            self.ptr = 0
+
+
 class Localizer:
     """One at_context: a shape (mics, frame length, lag range), its tables and streams on one GPU."""
 
@@ -123,6 +156,23 @@ class Localizer:
         L.check(self.lib.at_localize_host(self.ctx, C.c_void_p(_host_ptr(adc)),
                                           None if heads is None else C.c_void_p(_host_ptr(heads)), F, C.byref(o)))
         return res
+
+    def shared_alloc(self, nbytes):
+        """Device memory of this context's GPU that other processes can map (at_shared_alloc).  Returns a SharedArray."""
+        ptr, h = C.c_void_p(), C.create_string_buffer(64)
+        L.check(self.lib.at_shared_alloc(self.ctx, nbytes, C.byref(ptr), h))
+        return SharedArray(self, ptr.value, nbytes, h.raw, opened=False)
+
+    def shared_open(self, handle, nbytes):
+        """Map another process's SharedArray (its 64-byte .handle) for this context's GPU (at_shared_open)."""
+        ptr = C.c_void_p()
+        L.check(self.lib.at_shared_open(self.ctx, bytes(handle), C.byref(ptr)))
+        return SharedArray(self, ptr.value, nbytes, bytes(handle), opened=True)
+
+    def peer_enable(self, peer_device):
+        """Allow this context's kernels to store into memory of `peer_device` (frame-sharded runs write their results
+        straight into rank 0's arrays)."""
+        L.check(self.lib.at_peer_enable(self.ctx, int(peer_device)))
 
     def synchronize(self):
         L.check(self.lib.at_synchronize(self.ctx))

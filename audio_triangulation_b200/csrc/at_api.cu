@@ -346,6 +346,53 @@ extern "C" int at_synchronize(at_context *c)
     return AT_OK;
 }
 
+static_assert(sizeof(at_ipc_handle) == sizeof(cudaIpcMemHandle_t), "at_ipc_handle carries a cudaIpcMemHandle_t");
+extern "C" int at_shared_alloc(at_context *c, size_t bytes, void **d_ptr, at_ipc_handle *handle)
+{
+    if (!c || !d_ptr || !handle || !bytes) return fail(AT_EINVAL, "at_shared_alloc: bad argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMalloc(d_ptr, bytes));
+    CU(cudaMemset(*d_ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; return fail(AT_ECUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle->bytes, &h, sizeof h);
+    return AT_OK;
+}
+extern "C" int at_shared_open(at_context *c, const at_ipc_handle *handle, void **d_ptr)
+{
+    if (!c || !d_ptr || !handle) return fail(AT_EINVAL, "at_shared_open: bad argument");
+    CU(cudaSetDevice(c->cfg.device));       // the mapping is made for THIS device: peer access to the owner is enabled lazily
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->bytes, sizeof h);
+    const cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(AT_ECUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    return AT_OK;
+}
+extern "C" int at_shared_close(at_context *c, void *d_ptr, int opened)
+{
+    if (!c || !d_ptr) return AT_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaDeviceSynchronize());
+    if (opened) CU(cudaIpcCloseMemHandle(d_ptr));
+    else CU(cudaFree(d_ptr));
+    return AT_OK;
+}
+
+extern "C" int at_peer_enable(at_context *c, int peer_device)
+{
+    if (!c) return fail(AT_EINVAL, "at_peer_enable: null context");
+    if (peer_device == c->cfg.device) return AT_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, c->cfg.device, peer_device));
+    if (!can) return fail(AT_EINVAL, "device %d cannot access device %d", c->cfg.device, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return AT_OK; }
+    if (e != cudaSuccess) return fail(AT_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+    return AT_OK;
+}
+
 // ------------------------------------------------------------------ fused path, device API
 static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int kernel, cudaStream_t st)
 {

@@ -194,6 +194,17 @@ int at_localize_host(at_context *ctx, const uint8_t *h_adc, const int32_t *h_hea
 int at_localize_host_sharded(at_context **ctxs, int n_ctx, const uint8_t *h_adc, const int32_t *h_heads,
                              size_t n_frames, const at_outputs *h_out);
 int at_synchronize(at_context *ctx);
+/* Multi-GPU result placement (one process per GPU).  The rank that collects the results allocates its arrays with
+ * at_shared_alloc and hands the 64-byte handle to the other ranks (any channel: torch.distributed object broadcast, a
+ * pipe, a file); they map the arrays with at_shared_open and pass the returned pointers as at_outputs of their own
+ * at_localize_device calls.  Every rank's kernel then stores its slice of the results straight into the collector's
+ * memory over NVLink: a frame-sharded run needs no gather step and no collective in the data path.
+ * at_peer_enable: same idea inside one process (several contexts, one per GPU).  All idempotent / balanced by _close. */
+typedef struct at_ipc_handle { unsigned char bytes[64]; } at_ipc_handle;
+int at_shared_alloc(at_context *ctx, size_t bytes, void **d_ptr, at_ipc_handle *handle);
+int at_shared_open(at_context *ctx, const at_ipc_handle *handle, void **d_ptr);
+int at_shared_close(at_context *ctx, void *d_ptr, int opened /* 1: from at_shared_open, 0: from at_shared_alloc */);
+int at_peer_enable(at_context *ctx, int peer_device);
 
 /* Temporal stage for `n_arrays` independent arrays (ref: sample_compute.h:124-139,
  * correlations.c:38-63): where gate[i] != 0, estimate <- EMA(estimate, fresh) with the array's own

@@ -1,6 +1,6 @@
 """GPU, every visible device: frame-sharded runs must be byte-identical to a single-GPU run of the same batch
 (test pyramid item 3).  With one visible GPU the in-process test shards over two contexts of that GPU
-and the multi-process test is skipped."""
+and the multi-process test runs its two ranks on that GPU (same CUDA-IPC path)."""
 import ctypes as C
 import os
 import socket
@@ -45,26 +45,34 @@ def _rank(rank, world, port, F, q):
     (CUDA-IPC mapped), rank 0 then recomputes every slice on its own GPU."""
     import torch
     import torch.distributed as dist
-    from torch.multiprocessing.reductions import reduce_tensor
     import audio_triangulation_b200 as at
     from audio_triangulation_b200.sharding import frame_range
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    dev = torch.device("cuda", rank)
-    loc = at.Localizer(device=rank)
+    device = rank % torch.cuda.device_count()          # one GPU: both ranks share it (the IPC path is the same)
+    torch.cuda.set_device(device)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # only the handle exchange and barriers: CPU collectives
+    dev = torch.device("cuda", device)
+    loc = at.Localizer(device=device)
     lo, hi = frame_range(rank, world, world * F)
     adc, heads, _ = loc.synth_device(F, flags=2, first_frame=lo)
-    shapes = {"lags": ((F, 3), torch.int32), "cell": ((F,), torch.int32), "xy": ((F, 2), torch.float32)}
-    handles = [None]
+    shapes = {"lags": ((F, 3), torch.int32, 12), "cell": ((F,), torch.int32, 4), "xy": ((F, 2), torch.float32, 8)}
+    nbytes = world * F * 24
+    handle = [None]
+    if rank == 0:
+        shared = loc.shared_alloc(nbytes)
+        handle = [shared.handle]
+    dist.broadcast_object_list(handle, src=0)
+    if rank != 0:
+        shared = loc.shared_open(handle[0], nbytes)
+    off, base = {}, 0
+    for k, (_, _, bpf) in shapes.items():
+        off[k] = base
+        base += world * F * bpf
+    out = {k: shared.view(off[k] + rank * F * bpf, F * bpf) for k, (_, _, bpf) in shapes.items()}
     glob = None
     if rank == 0:
-        glob = {k: torch.zeros((world,) + s, dtype=d, device=dev) for k, (s, d) in shapes.items()}
-        handles = [{k: reduce_tensor(v) for k, v in glob.items()}]
-    dist.broadcast_object_list(handles, src=0)
-    if rank != 0:
-        glob = {k: fn(*a) for k, (fn, a) in handles[0].items()}
-    out = {k: v[rank] for k, v in glob.items()}
+        whole = shared.tensor()
+        glob = {k: whole[off[k]: off[k] + world * F * bpf].view(d).view((world,) + sh) for k, (sh, d, bpf) in shapes.items()}
     loc.localize_device(adc, heads, want=WANT, out=out)
     torch.cuda.synchronize(dev)
     dist.barrier()
@@ -78,15 +86,18 @@ def _rank(rank, world, port, F, q):
             ok = ok and all(bool(torch.equal(chk[k].view(torch.uint8), glob[k][r].view(torch.uint8))) for k in WANT)
         q.put(ok)
     dist.barrier()
-    del out, glob
+    if rank != 0:
+        shared.close()
+    dist.barrier()
+    if rank == 0:
+        del glob
+        shared.close()
     dist.destroy_process_group()
 
 
 def test_peer_stores_into_rank0_equal_single_gpu():
     torch = _torch()
-    world = min(torch.cuda.device_count(), 8)
-    if world < 2:
-        pytest.skip("needs at least two GPUs")
+    world = max(2, min(torch.cuda.device_count(), 8))
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
