@@ -5,6 +5,6 @@ This package is the thin host-side mirror used by tests and bench.py: torch supp
 memory and streams, nothing else.
 """
 from ._lib import AtError, load  # noqa: F401
-from .api import Localizer, Stream, dropin  # noqa: F401
+from .api import Localizer, Stream, dropin, hemisphere_points  # noqa: F401
 
-__all__ = ["Localizer", "Stream", "dropin", "load", "AtError"]
+__all__ = ["Localizer", "Stream", "dropin", "hemisphere_points", "load", "AtError"]

@@ -15,6 +15,7 @@ AT_OK, AT_EINVAL, AT_ECUDA, AT_ENOGPU, AT_ENOMEM = 0, -1, -2, -3, -4
 AT_MAX_MICS = 8
 KERNELS = {"auto": 0, "imad": 1, "imma": 2, "umma": 4}
 AT_CORR_PACKED, AT_CORR_STRUCT = 0, 1
+AT_LUT_PLANE, AT_LUT_POINTS = 0, 1
 SYNTH_INTEGER_DELAYS, SYNTH_RANDOM_HEADS, SYNTH_KATS, SYNTH_MAX_NOISE, SYNTH_WHITE = 1, 2, 4, 8, 16
 UBENCH = {"imad_wide": 0, "imad": 1, "dp2a": 2, "dp4a": 3, "imma_s8": 4, "lds": 5, "dfma": 6, "umma_i8": 7, "umma_frame": 8}
 
@@ -26,7 +27,8 @@ class AtConfig(C.Structure):
                 ("half_w", C.c_int32), ("half_h", C.c_int32),
                 ("px_per_m", C.c_float), ("height_m", C.c_float),
                 ("use_reference_triangle", C.c_int32),
-                ("mic_xy", (C.c_float * 2) * AT_MAX_MICS)]
+                ("mic_xy", (C.c_float * 2) * AT_MAX_MICS),
+                ("lut_mode", C.c_int32), ("n_points", C.c_int32), ("points_xyz", C.c_void_p)]
 
 
 class AtOutputs(C.Structure):
@@ -59,6 +61,7 @@ def load():
     ctx = C.c_void_p
     protos = {
         "at_config_reference": (None, [C.POINTER(AtConfig)]),
+        "at_hemisphere_points": (None, [C.c_int, C.c_int, C.c_float, vp]),
         "at_create": (C.c_int, [C.POINTER(AtConfig), C.POINTER(ctx)]),
         "at_destroy": (None, [ctx]),
         "at_last_error": (C.c_char_p, []),

@@ -23,6 +23,13 @@ def _np_ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+def hemisphere_points(n_az, n_el, radius_m):
+    """n_az x n_el directions on the upper hemisphere (at_hemisphere_points): float32 [n_el * n_az, 3]."""
+    xyz = np.zeros((n_el * n_az, 3), np.float32)
+    L.load().at_hemisphere_points(n_az, n_el, C.c_float(radius_m), C.c_void_p(xyz.ctypes.data))
+    return xyz
+
+
 class DevPtr:
     """A raw device pointer where the API takes a tensor (only .data_ptr() is used)."""
 
@@ -61,7 +68,9 @@ class Localizer:
 
     def __init__(self, device=0, n_mics=3, n_bits=10, max_shift=46, kernel="auto", mic_xy=None,
                  sample_rate_hz=50000.0, speed_of_sound=343.0, half_w=50, half_h=50, px_per_m=24.0,
-                 height_m=1.2):
+                 height_m=1.2, points=None):
+        """points: optional float32 [n, 3] candidate source positions (AT_LUT_POINTS, the 3-D form of the lag look-up
+        table, e.g. hemisphere_points()); default: the reference's plane-on-sphere grid."""
         self.lib = L.load()
         cfg = L.AtConfig()
         self.lib.at_config_reference(C.byref(cfg))
@@ -79,6 +88,9 @@ class Localizer:
             for m in range(min(n_mics, L.AT_MAX_MICS)):
                 ang = 2.0 * np.pi * m / n_mics
                 cfg.mic_xy[m][0], cfg.mic_xy[m][1] = float(np.float32(0.1 * np.cos(ang))), float(np.float32(0.1 * np.sin(ang)))
+        if points is not None:
+            self._points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+            cfg.lut_mode, cfg.n_points, cfg.points_xyz = L.AT_LUT_POINTS, self._points.shape[0], self._points.ctypes.data
         self.cfg = cfg
         self.ctx = C.c_void_p()
         L.check(self.lib.at_create(C.byref(cfg), C.byref(self.ctx)))

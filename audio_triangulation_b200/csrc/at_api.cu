@@ -80,6 +80,7 @@ struct at_context {
     int16_t *d_window = nullptr; float *d_gauss = nullptr; int32_t *d_delay_q8 = nullptr;
     // host copies
     std::vector<float> h_mic_xy; std::vector<uint8_t> h_lut; std::vector<int32_t> h_delay_q8;
+    std::vector<float> h_points;   // AT_LUT_POINTS: candidate positions [cells][3]
     // staging for the host API and the drop-in symbols
     HostSlot slot[2];
     void *d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -99,6 +100,17 @@ static int ensure(void **p, size_t bytes)
     if (*p) return AT_OK;
     CU(cudaMalloc(p, bytes));
     return AT_OK;
+}
+
+extern "C" void at_hemisphere_points(int n_az, int n_el, float radius_m, float *xyz)
+{
+    const double pi = 3.14159265358979323846;
+    for (int e = 0; e < n_el; e++)
+        for (int a = 0; a < n_az; a++) {
+            const double az = 2.0 * pi * a / n_az, el = (e + 0.5) / n_el * (pi / 2);
+            float *p = xyz + 3 * ((size_t)e * n_az + a);
+            p[0] = (float)(radius_m * cos(el) * cos(az)); p[1] = (float)(radius_m * cos(el) * sin(az)); p[2] = (float)(radius_m * sin(el));
+        }
 }
 
 extern "C" void at_config_reference(at_config *c)
@@ -163,7 +175,10 @@ static int create_impl(const at_config *cfg, at_context *c)
     c->n_pairs = M * (M - 1) / 2;
     c->n_samples = 1 << cfg->n_bits;
     c->n_lags = 2 * L + 1;
-    c->n_cells = (2 * cfg->half_w + 1) * (2 * cfg->half_h + 1);
+    const bool points = cfg->lut_mode == AT_LUT_POINTS;
+    if (points && (cfg->n_points < 1 || cfg->n_points > (1 << 22) || !cfg->points_xyz))
+        return fail(AT_EINVAL, "AT_LUT_POINTS needs 1..4194304 candidate positions");
+    c->n_cells = points ? cfg->n_points : (2 * cfg->half_w + 1) * (2 * cfg->half_h + 1);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &s : c->slot) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
 
@@ -175,10 +190,21 @@ static int create_impl(const at_config *cfg, at_context *c)
         CU(cudaMemcpyAsync(c->d_mic_xy, cfg->mic_xy, sizeof(float) * 2 * M, cudaMemcpyHostToDevice, c->stream));
     }
     CU(cudaMalloc(&c->d_lut, (size_t)c->n_pairs * c->n_cells));
-    CU(at_launch_lut_build(c->d_mic_xy, M, L, cfg->sample_rate_hz, cfg->speed_of_sound, cfg->half_w, cfg->half_h,
-                           cfg->px_per_m, cfg->height_m, c->d_lut, c->stream));
     CU(cudaMalloc(&c->d_cell_xy, sizeof(float2) * c->n_cells));
-    CU(at_launch_cell_xy(cfg->half_w, cfg->half_h, cfg->px_per_m, c->d_cell_xy, c->stream));
+    if (points) {   // the 3-D form of the table: arbitrary candidate positions
+        c->h_points.assign(cfg->points_xyz, cfg->points_xyz + 3 * (size_t)c->n_cells);
+        float *d_points = nullptr;
+        CU(cudaMalloc(&d_points, sizeof(float) * c->h_points.size()));
+        CU(cudaMemcpyAsync(d_points, c->h_points.data(), sizeof(float) * c->h_points.size(), cudaMemcpyHostToDevice, c->stream));
+        CU(at_launch_lut_points(c->d_mic_xy, M, L, cfg->sample_rate_hz, cfg->speed_of_sound, d_points, c->n_cells, c->d_lut,
+                                c->d_cell_xy, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d_points);
+    } else {
+        CU(at_launch_lut_build(c->d_mic_xy, M, L, cfg->sample_rate_hz, cfg->speed_of_sound, cfg->half_w, cfg->half_h,
+                               cfg->px_per_m, cfg->height_m, c->d_lut, c->stream));
+        CU(at_launch_cell_xy(cfg->half_w, cfg->half_h, cfg->px_per_m, c->d_cell_xy, c->stream));
+    }
     c->h_mic_xy.resize(2 * M);
     c->h_lut.resize((size_t)c->n_pairs * c->n_cells);
     CU(cudaMemcpyAsync(c->h_mic_xy.data(), c->d_mic_xy, sizeof(float) * 2 * M, cudaMemcpyDeviceToHost, c->stream));
@@ -284,16 +310,22 @@ static int create_impl(const at_config *cfg, at_context *c)
         const int W = 2 * cfg->half_w + 1;
         c->h_delay_q8.resize((size_t)c->n_cells * M);
         for (int cell = 0; cell < c->n_cells; cell++) {
-            double x = (cell % W - cfg->half_w) / (double)cfg->px_per_m;
-            double y = (cfg->half_h - cell / W) / (double)cfg->px_per_m;
-            double z = cfg->height_m;
-            const double k = cfg->height_m / sqrt(x * x + y * y + z * z);
-            x *= k; y *= k; z *= k;
+            double x, y, z, ref;
+            if (points) {   // delays relative to the candidate's distance from the array centre
+                x = c->h_points[3 * (size_t)cell]; y = c->h_points[3 * (size_t)cell + 1]; z = c->h_points[3 * (size_t)cell + 2];
+                ref = sqrt(x * x + y * y + z * z);
+            } else {
+                x = (cell % W - cfg->half_w) / (double)cfg->px_per_m;
+                y = (cfg->half_h - cell / W) / (double)cfg->px_per_m;
+                z = cfg->height_m;
+                const double k = cfg->height_m / sqrt(x * x + y * y + z * z);
+                x *= k; y *= k; z *= k;
+                ref = cfg->height_m;
+            }
             for (int m = 0; m < M; m++) {
                 const double dx = x - c->h_mic_xy[2 * m], dy = y - c->h_mic_xy[2 * m + 1];
                 const double dist = sqrt(dx * dx + dy * dy + z * z);
-                c->h_delay_q8[(size_t)cell * M + m] =
-                    (int32_t)llround(256.0 * (dist - cfg->height_m) / cfg->speed_of_sound * cfg->sample_rate_hz);
+                c->h_delay_q8[(size_t)cell * M + m] = (int32_t)llround(256.0 * (dist - ref) / cfg->speed_of_sound * cfg->sample_rate_hz);
             }
         }
         CU(cudaMalloc(&c->d_delay_q8, sizeof(int32_t) * c->h_delay_q8.size()));
@@ -301,6 +333,7 @@ static int create_impl(const at_config *cfg, at_context *c)
     }
     c->scratch_bytes = 1 << 16;
     CU(cudaMalloc(&c->d_scratch, c->scratch_bytes));
+    c->cfg.points_xyz = nullptr;     // the caller's array was read above and is not retained
     return AT_OK;
 }
 
@@ -665,7 +698,7 @@ extern "C" int at_heatmap_device(at_context *c, const int64_t *d_corr, size_t n_
     if (!c || !d_corr) return fail(AT_EINVAL, "at_heatmap_device: null argument");
     CU(cudaSetDevice(c->cfg.device));
     CU(at_launch_heatmap((const long long *)d_corr, n_arrays, c->n_pairs, c->cfg.max_shift, c->d_lut, c->d_cand_idx,
-                         c->d_cand_cell, c->n_cand, c->n_cells, c->cfg.half_w, c->cfg.half_h, c->cfg.px_per_m, d_cell,
+                         c->d_cand_cell, c->n_cand, c->n_cells, c->d_cell_xy, d_cell,
                          (long long *)d_highest, d_xy, d_classes, (cudaStream_t)stream));
     return AT_OK;
 }

@@ -59,6 +59,28 @@ __global__ void lut_build_kernel(const float *mic_xy, int n_mics, int L, float r
         }
 }
 
+// The general (3-D) form of the table: candidate positions are given, everything after vga_heatmap.h:60 is the reference's
+// arithmetic unchanged (distances :63-65, time differences :68-70, roundf :72-74, clamp :76-87, index :88-90).
+__global__ void lut_points_kernel(const float *mic_xy, int n_mics, int L, float rate_hz, float speed, const float *points,
+                                  int n_points, uint8_t *lut, float2 *xy)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_points) return;
+    const float xm = points[3 * c], ym = points[3 * c + 1], zm = points[3 * c + 2];
+    float dist[AT_MAX_MICS_I];
+    for (int m = 0; m < n_mics; m++)
+        dist[m] = norm3(zm, __fsub_rn(xm, mic_xy[2 * m]), __fsub_rn(ym, mic_xy[2 * m + 1]));
+    int p = 0;
+    for (int i = 0; i < n_mics; i++)
+        for (int j = i + 1; j < n_mics; j++, p++) {
+            const float dt = __fdiv_rn(__fsub_rn(dist[j], dist[i]), speed);
+            int s = (int)roundf(__fmul_rn(dt, rate_hz));
+            s = s < -L ? -L : (s > L ? L : s);
+            lut[(size_t)p * n_points + c] = (uint8_t)(s + L);
+        }
+    xy[c] = make_float2(xm, ym);
+}
+
 // ref: components/vga/vga_heatmap.h:52-53 -- plane coordinates of every cell (IEEE division, as the host does)
 __global__ void cell_xy_kernel(int half_w, int half_h, float px_per_m, float2 *xy)
 {
@@ -169,8 +191,8 @@ __global__ void admissible_lags_kernel(const long long *curves, size_t n_items, 
 // ------------------------------------------------------------------ stand-alone likelihood map
 // ref: components/vga/vga_heatmap.h:96-126 for arbitrary curves; one block per array.
 __global__ void heatmap_kernel(const long long *corr, int n_pairs, int L, const uint8_t *lut, const uint8_t *cand_idx,
-                               const int32_t *cand_cell, int n_cand, int n_cells, int half_w, int half_h,
-                               float px_per_m, int32_t *cell, long long *highest, float *xy, uint8_t *classes)
+                               const int32_t *cand_cell, int n_cand, int n_cells, const float2 *cell_xy,
+                               int32_t *cell, long long *highest, float *xy, uint8_t *classes)
 {
     extern __shared__ long long curve[];   // [P][NL]
     __shared__ long long red_v[32];
@@ -198,9 +220,8 @@ __global__ void heatmap_kernel(const long long *corr, int n_pairs, int L, const 
             if (cell) cell[a] = ci;
             if (highest) highest[a] = r.v;
             if (xy) {
-                const int W = 2 * half_w + 1;
-                xy[2 * a] = __fdiv_rn((float)(ci % W - half_w), px_per_m);
-                xy[2 * a + 1] = __fdiv_rn((float)(half_h - ci / W), px_per_m);
+                xy[2 * a] = cell_xy[ci].x;        // vga_heatmap.h:52-53, tabulated per cell (or the candidate point's x, y)
+                xy[2 * a + 1] = cell_xy[ci].y;
             }
         }
     }
@@ -461,6 +482,14 @@ cudaError_t at_launch_lut_build(const float *d_mic_xy, int n_mics, int L, float 
     return cudaGetLastError();
 }
 
+cudaError_t at_launch_lut_points(const float *d_mic_xy, int n_mics, int L, float rate_hz, float speed, const float *d_points,
+                                 int n_points, uint8_t *d_lut, float2 *d_xy, cudaStream_t st)
+{
+    lut_points_kernel<<<(n_points + 127) / 128, 128, 0, st>>>(d_mic_xy, n_mics, L, rate_hz, speed, d_points, n_points, d_lut, d_xy);
+    at_count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t at_launch_cell_xy(int half_w, int half_h, float px_per_m, float2 *d_xy, cudaStream_t st)
 {
     const int cells = (2 * half_w + 1) * (2 * half_h + 1);
@@ -516,14 +545,13 @@ cudaError_t at_launch_admissible_lags(const long long *d_curves, size_t n_frames
 
 cudaError_t at_launch_heatmap(const long long *d_corr, size_t n_arrays, int n_pairs, int L, const uint8_t *d_lut,
                               const uint8_t *d_cand_idx, const int32_t *d_cand_cell, int n_cand, int n_cells,
-                              int half_w, int half_h, float px_per_m, int32_t *d_cell, long long *d_highest,
+                              const float2 *d_cell_xy, int32_t *d_cell, long long *d_highest,
                               float *d_xy, uint8_t *d_classes, cudaStream_t st)
 {
     if (!n_arrays) return cudaSuccess;
     const int smem = n_pairs * (2 * L + 1) * (int)sizeof(long long);
     heatmap_kernel<<<(unsigned)n_arrays, 256, smem, st>>>(d_corr, n_pairs, L, d_lut, d_cand_idx, d_cand_cell, n_cand,
-                                                          n_cells, half_w, half_h, px_per_m, d_cell, d_highest, d_xy,
-                                                          d_classes);
+                                                          n_cells, d_cell_xy, d_cell, d_highest, d_xy, d_classes);
     at_count_launch();
     return cudaGetLastError();
 }

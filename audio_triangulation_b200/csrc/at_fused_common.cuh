@@ -278,12 +278,7 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
             e.red_v[0] = r.v;
             if (p.cell) p.cell[f] = cellidx;
             if (p.highest) p.highest[f] = r.v;
-            if (p.xy) {
-                const int W = 2 * p.half_w + 1;
-                const int cy = cellidx / W, cx = cellidx % W;
-                p.xy[2 * f + 0] = __fdiv_rn((float)(cx - p.half_w), p.px_per_m);   // vga_heatmap.h:52
-                p.xy[2 * f + 1] = __fdiv_rn((float)(p.half_h - cy), p.px_per_m);   // vga_heatmap.h:53
-            }
+            if (p.xy) reinterpret_cast<float2 *>(p.xy)[f] = p.cell_xy[cellidx];   // vga_heatmap.h:52-53, tabulated per cell
         }
     }
     if (p.classes) {   // vga_heatmap.h:111-126, colour codes of lib/vga/vga16_graphics.h:31-34

@@ -74,6 +74,9 @@ cudaError_t at_launch_lut_build(const float *d_mic_xy, int n_mics, int L, float 
                                 int half_w, int half_h, float px_per_m, float height, uint8_t *d_lut,
                                 cudaStream_t st);
 cudaError_t at_launch_cell_xy(int half_w, int half_h, float px_per_m, float2 *d_xy, cudaStream_t st);
+// AT_LUT_POINTS: the same table for arbitrary 3-D candidate positions d_points [n_points][3]; also fills d_xy with their (x, y)
+cudaError_t at_launch_lut_points(const float *d_mic_xy, int n_mics, int L, float rate_hz, float speed, const float *d_points,
+                                 int n_points, uint8_t *d_lut, float2 *d_xy, cudaStream_t st);
 cudaError_t at_launch_write_out(const int16_t *d_ring, int head, int n_bits, int16_t *d_out, long long *d_power,
                                 cudaStream_t st);
 cudaError_t at_launch_shift8(int16_t *d_x, int n, cudaStream_t st);
@@ -84,7 +87,7 @@ cudaError_t at_launch_average(long long *d_est, int32_t *d_est_best, unsigned lo
                               cudaStream_t st);
 cudaError_t at_launch_heatmap(const long long *d_corr, size_t n_arrays, int n_pairs, int L,
                               const uint8_t *d_lut, const uint8_t *d_cand_idx, const int32_t *d_cand_cell,
-                              int n_cand, int n_cells, int half_w, int half_h, float px_per_m,
+                              int n_cand, int n_cells, const float2 *d_cell_xy,
                               int32_t *d_cell, long long *d_highest, float *d_xy, uint8_t *d_classes,
                               cudaStream_t st);
 cudaError_t at_launch_admissible_lags(const long long *d_curves, size_t n_frames, int n_pairs, int L, const int32_t *d_lmax,

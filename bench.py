@@ -310,6 +310,30 @@ def run_ours(args):
             extra["random_ring_heads"] = time_device(loc, torch, stream, hadc, hheads, WANT, k)
             del hadc, hheads
             extra["certified_frac"] = (search or {}).get("lags_certified_without_ll_product")
+            # BASELINE configs[3] and [4] (no reference counterpart; parity against the generalised oracle only)
+            try:
+                loc8 = at.Localizer(device=local_rank, n_mics=8, n_bits=12, max_shift=46, points=at.hemisphere_points(72, 12, 2.0))
+                F8 = 1 << 14                       # 512 MB of input: larger than L2
+                adc8, _, _ = loc8.synth_device(F8)
+                torch.cuda.synchronize(dev)
+                extra["config4"] = {"workload": "8 mics x 4096 samples, 28 pairs, +-46 lags, direct fixed-point xcorr on tcgen05; "
+                                                "position = arg-max over 72 x 12 hemisphere directions",
+                                    "frames": F8,
+                                    "lags_frames_per_s": time_device(loc8, torch, stream, adc8, None, ("lags",), k),
+                                    "lags_position_frames_per_s": time_device(loc8, torch, stream, adc8, None, ("lags", "cell", "xy"), k),
+                                    "int16_tmac_per_s": None}
+                extra["config4"]["int16_tmac_per_s"] = extra["config4"]["lags_frames_per_s"] * 28 * (93 * 4096 - 2162) / 1e12
+                del adc8
+                loc8.close()
+            except Exception as e:   # pragma: no cover
+                extra["config4"] = {"error": str(e)}
+            try:
+                import subprocess
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stream_bench.py"), "--blocks", "20"],
+                                   capture_output=True, text=True, timeout=240)
+                extra["config5"] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:   # pragma: no cover
+                extra["config5"] = {"error": str(e)}
 
         # ---- roofline of the dominant kernel
         ubench = {}

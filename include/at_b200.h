@@ -141,7 +141,21 @@ typedef struct at_config {
     /* microphone coordinates in metres; n_mics == 3 && use_reference_triangle -> microphones_init() geometry */
     int32_t use_reference_triangle;
     float mic_xy[AT_MAX_MICS][2];
+    /* Candidate source positions of the lag look-up table.  AT_LUT_PLANE (default): the reference's set, the half_w x
+     * half_h grid of the z = height_m plane projected onto the sphere of radius height_m (vga_heatmap.h:50-60).
+     * AT_LUT_POINTS: `n_points` arbitrary 3-D positions (x, y, z in metres, microphones in the z = 0 plane), e.g. a
+     * hemisphere of directions (at_hemisphere_points) or a volume grid -- the general, 3-D form of the same table: expected
+     * lag of pair (i, j) = roundf((|p - m_j| - |p - m_i|) / c * fs), clamped to +-L.  `cell` outputs then index the points,
+     * `xy` holds their (x, y), `classes` has n_points entries. */
+    int32_t lut_mode;
+    int32_t n_points;
+    const float *points_xyz;   /* [n_points][3], host memory, read by at_create only */
 } at_config;
+#define AT_LUT_PLANE 0
+#define AT_LUT_POINTS 1
+/* n_az x n_el directions on the upper hemisphere of radius `radius_m` (azimuth 2 pi a / n_az; elevation from the horizon
+ * towards the zenith, (e + 0.5) / n_el * pi / 2), row-major [n_el][n_az][3].  A convenience for AT_LUT_POINTS. */
+void at_hemisphere_points(int n_az, int n_el, float radius_m, float *xyz);
 
 typedef struct at_context at_context;
 

@@ -210,6 +210,27 @@ void ato_lut_build(const float *mic_xy, int n_mics, int L, float rate_hz, float 
     free(dist);
 }
 
+/* vga_heatmap.h:63-90 with the candidate position given (3-D candidate sets: hemisphere of directions, volume grid) */
+void ato_lut_build_points(const float *mic_xy, int n_mics, int L, float rate_hz, float speed,
+                          const float *points, int n_points, uint8_t *idx)
+{
+    float *dist = malloc(sizeof(float) * (size_t)n_mics);
+    for (int c = 0; c < n_points; c++) {
+        const float xm = points[3 * c], ym = points[3 * c + 1], zm = points[3 * c + 2];
+        for (int m = 0; m < n_mics; m++)
+            dist[m] = norm3(zm, xm - mic_xy[2 * m], ym - mic_xy[2 * m + 1]);
+        int p = 0;
+        for (int i = 0; i < n_mics; i++)
+            for (int j = i + 1; j < n_mics; j++, p++) {
+                const float dt = (dist[j] - dist[i]) / speed;
+                int s = (int)roundf(dt * rate_hz);
+                if (s < -L) s = -L; else if (s > L) s = L;
+                idx[(size_t)p * n_points + c] = (uint8_t)(s + L);
+            }
+    }
+    free(dist);
+}
+
 /* components/vga/vga_heatmap.h:96-126 -- L(cell) = sum over pairs of corr[pair][lut[pair][cell]];
  * its maximum (strict '>' in row-major order; we also return the first cell reaching it);
  * thresholds 63/64, 31/32, 15/16, 7/8 via multiply + arithmetic shift (:111-114);

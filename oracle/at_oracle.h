@@ -51,6 +51,11 @@ void ato_lut_build(const float *mic_xy, int n_mics, int L, float rate_hz, float 
                    int half_w, int half_h, float px_per_m, float height,
                    uint8_t *idx /*[pairs][2*half_h+1][2*half_w+1]*/);
 
+/* the same table for arbitrary 3-D candidate positions points[n][3] (no reference counterpart: the general form of
+ * vga_heatmap.h:63-90 with the candidate given instead of derived from a pixel) */
+void ato_lut_build_points(const float *mic_xy, int n_mics, int L, float rate_hz, float speed,
+                          const float *points, int n_points, uint8_t *idx /*[pairs][n_points]*/);
+
 /* ---- likelihood map (vga_heatmap.h:96-126).  classes may be NULL. ---- */
 void ato_heatmap(const int64_t *corr /*[pairs][2L+1]*/, const uint8_t *idx, int n_pairs,
                  int n_cells, int L, int64_t *highest, int32_t *first_cell, uint8_t *classes);

@@ -61,6 +61,7 @@ def load_oracle():
     lib.ato_mics_triangle.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, f32p]
     lib.ato_lut_build.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                   C.c_float, C.c_float, u8p]
+    lib.ato_lut_build_points.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, f32p, C.c_int, u8p]
     lib.ato_heatmap.argtypes = [i64p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ato_synth_frames.argtypes = [C.c_uint64, C.c_uint32, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.ato_synth_plain.argtypes = [C.c_int]

@@ -445,6 +445,57 @@ def test_bounded_search_paths_are_exercised(kernel, oracle):
     assert st2[:4].sum() == adc.shape[0] and 0 < st2[4] <= st2[3] and st2[4] < adc.shape[0], st2
 
 
+# ---------------------------------------------------------------- 3-D candidate sets (no reference pin beyond the table's arithmetic)
+def test_points_lut_reference_candidates_equal_reference_table(golden_hm):
+    """AT_LUT_POINTS with the reference's own candidate positions gives the reference's table (and the same cells)."""
+    import audio_triangulation_b200 as at
+    torch = _torch()
+    f = np.float32
+    y, x = np.divmod(np.arange(CELLS), 101)
+    xm = (x - 50).astype(f) / f(24.0); ym = (50 - y).astype(f) / f(24.0); zm = np.full(CELLS, 1.2, f)
+    k = f(1.2) / np.sqrt(zm * zm + xm * xm + ym * ym, dtype=f)
+    pts = np.stack([xm * k, ym * k, zm * k], 1).astype(f)
+    loc = at.Localizer(device=0, points=pts)
+    assert (loc.lut() == golden_hm["lut"]).all()
+    ref = at.Localizer(device=0)
+    adc, heads, _ = ref.synth_device(600, flags=2 | 4)
+    a = loc.localize_device(adc, heads, want=("lags", "cell", "highest")); b = ref.localize_device(adc, heads, want=("lags", "cell", "highest"))
+    torch.cuda.synchronize()
+    for k_ in ("lags", "cell", "highest"):
+        assert torch.equal(a[k_], b[k_]), k_
+
+
+def test_hemisphere_lut_8_mics_position(oracle):
+    """Config 4 gets a position: 8 microphones x 4096 samples (28 pairs), candidate directions on a hemisphere (azimuth x
+    elevation at 2 m), likelihood arg-max over the 28 curves inside the tcgen05 kernel's epilogue.  Table, cell and
+    highest_L equal the oracle's restatement; the synthetic sources are found."""
+    import audio_triangulation_b200 as at
+    torch = _torch()
+    n_az, n_el, R = 72, 12, 2.0
+    pts = at.hemisphere_points(n_az, n_el, R)
+    M, nb, Ls = 8, 12, 46
+    loc = at.Localizer(device=0, n_mics=M, n_bits=nb, max_shift=Ls, points=pts)
+    mics = loc.mics()
+    P, n = M * (M - 1) // 2, pts.shape[0]
+    idx = np.zeros((P, n), np.uint8)
+    oracle.lib.ato_lut_build_points(mics.reshape(-1), M, Ls, 50000.0, 343.0, pts.reshape(-1), n, idx.reshape(-1))
+    assert (loc.lut() == idx).all()
+    F = 96
+    adc, heads, truth = loc.synth_device(F, flags=2, seed=11)
+    r = loc.localize_device(adc, heads, want=("lags", "cell", "highest", "xy"))
+    torch.cuda.synchronize()
+    o = Oracle(n_mics=M, n_bits=nb, max_shift=Ls, lut=idx, n_cells=n).localize(adc.cpu().numpy(), heads=heads.cpu().numpy(),
+                                                                               want_corr=False, nthreads=16)
+    assert (r["lags"].cpu().numpy() == o["lags"]).all()
+    assert (r["cell"].cpu().numpy() == o["cell"]).all() and (r["highest"].cpu().numpy() == o["highest"]).all()
+    cell = r["cell"].cpu().numpy(); t = truth.cpu().numpy()
+    assert (r["xy"].cpu().numpy().view(np.uint32) == pts[cell][:, :2].view(np.uint32)).all()
+    # direction error: angle between the estimated and the true unit vectors (a planar array resolves azimuth well and
+    # elevation coarsely; most estimates must fall within 15 degrees)
+    cosang = (pts[cell] * pts[t]).sum(1) / (R * R)
+    assert (np.degrees(np.arccos(np.clip(cosang, -1, 1))) < 15.0).mean() > 0.7
+
+
 # ---------------------------------------------------------------- other shapes (no reference pin)
 @pytest.mark.parametrize("shape", [(8, 12, 46, 1500), (8, 10, 46, 6000)])
 def test_umma_8mic_large_batch_equals_mma_sync_kernel(shape):

@@ -144,3 +144,17 @@ def test_host_generator_self_consistent(oracle):
     assert (a[0, 0] == 128).all() and (a[0, 1] == 131).all()          # frame 0 = the silence KAT
     c, _, _ = oracle.synth(100, first_frame=500, flags=2 | 4)
     assert (c == a[500:]).all()                                       # counter-based: any sub-range gives the same frames
+
+
+def test_points_lut_reduces_to_the_reference_lut(oracle, golden_hm):
+    """The 3-D form of the lag look-up table (arbitrary candidate positions, ato_lut_build_points) fed with the reference's
+    own candidate set -- the 101 x 101 plane grid projected onto the 1.2 m sphere, in the reference's float32 arithmetic
+    (vga_heatmap.h:52-60) -- must reproduce the reference's table bit for bit."""
+    f = np.float32
+    y, x = np.divmod(np.arange(CELLS), 101)
+    xm = (x - 50).astype(f) / f(24.0); ym = (50 - y).astype(f) / f(24.0); zm = np.full(CELLS, 1.2, f)
+    k = f(1.2) / np.sqrt(zm * zm + xm * xm + ym * ym, dtype=f)       # hypot3f(z, x, y): same summation order
+    pts = np.ascontiguousarray(np.stack([xm * k, ym * k, zm * k], 1), f)
+    idx = np.zeros((3, CELLS), np.uint8)
+    oracle.lib.ato_lut_build_points(oracle.mics().reshape(-1), 3, L, 50000.0, 343.0, pts.reshape(-1), CELLS, idx.reshape(-1))
+    assert (idx == golden_hm["lut"]).all()

@@ -28,6 +28,13 @@ KEEP = [
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__cycles_active.sum",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
 ]
 
 
@@ -55,6 +62,7 @@ def main():
             d["derived"] = {"frames_per_launch": frames, "frames_per_s": frames / (t_ms * 1e-3),
                             "warp_instr_per_frame": d["smsp__inst_executed.sum"]["value"] / frames,
                             "smem_wavefronts_per_frame": d["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]["value"] / frames,
+                            "tensor_operand_wavefronts_per_frame": d.get("l1tex__data_pipe_tc_wavefronts_mem_shared.sum", {"value": 0})["value"] / frames,
                             "dram_bytes_per_frame": (_b(d["dram__bytes_read.sum"]) + _b(d["dram__bytes_write.sum"])) / frames,
                             "dram_bytes_per_launch": _b(d["dram__bytes_read.sum"]) + _b(d["dram__bytes_write.sum"])}
         res.append(d)
