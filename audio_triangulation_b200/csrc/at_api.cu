@@ -163,6 +163,12 @@ static int create_impl(const at_config *cfg, at_context *c)
     if (M < 2 || M > AT_MAX_MICS || cfg->n_bits < 8 || cfg->n_bits > 12 || L < 1 || L > 127 ||
         cfg->half_w < 0 || cfg->half_h < 0 || cfg->half_w > 512 || cfg->half_h > 512)
         return fail(AT_EINVAL, "unsupported shape: mics=%d n_bits=%d max_shift=%d", M, cfg->n_bits, L);
+    {   // a shape no fused kernel is instantiated for would only fail at the first at_localize_*: refuse it here
+        const AtShape sh = {M, cfg->n_bits, L};
+        const bool any = at_fused_imad_supports(sh) || at_fused_imma_supports(sh) || at_fused_imma_cta_supports(sh) ||
+                         at_fused_umma_supports(sh) || at_fused_umma_m_supports(sh);
+        if (!any) return fail(AT_EINVAL, "no kernel instantiation for mics=%d n_bits=%d max_shift=%d", M, cfg->n_bits, L);
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device)
         return fail(AT_ENOGPU, "no CUDA device %d (found %d): libat_b200 has no CPU fallback", cfg->device, ndev);
@@ -267,7 +273,7 @@ static int create_impl(const at_config *cfg, at_context *c)
         // 3 pairs: direct table over the whole (i0, i1, i2) cube -> first cell of that tuple and its plane
         // coordinates, so that a frame whose three peaks form a tuple of the LUT is settled by one load
         // (index bookkeeping only; 16 bytes x NL^3 = 12.9 MB at NL = 93, only the ~2.5 k present tuples are ever hot)
-        if (P == 3) {
+        if (P == 3 && (at_fused_imma_supports({M, cfg->n_bits, L}) || at_fused_umma_supports({M, cfg->n_bits, L}))) {
             std::vector<float2> xy((size_t)c->n_cells);
             CU(cudaMemcpy(xy.data(), c->d_cell_xy, sizeof(float2) * xy.size(), cudaMemcpyDeviceToHost));
             std::vector<int4> tab((size_t)NLg * NLg * NLg, make_int4(-1, 0, 0, 0));
@@ -620,8 +626,12 @@ extern "C" int at_localize_host(at_context *c, const uint8_t *h_adc, const int32
     if (!c || !o || (!h_adc && n_frames)) return fail(AT_EINVAL, "at_localize_host: null argument");
     if (!n_frames) return AT_OK;
     const int rc = host_async(c, h_adc, h_heads, n_frames, o);
+    // also on an error: copies into the caller's host arrays may be in flight from the chunks already launched
+    int rc_sync = AT_OK;
+    for (auto &s : c->slot)
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess) rc_sync = AT_ECUDA;
     if (rc != AT_OK) return rc;
-    for (auto &s : c->slot) CU(cudaStreamSynchronize(s.stream));
+    if (rc_sync != AT_OK) return fail(AT_ECUDA, "at_localize_host: %s", cudaGetErrorString(cudaGetLastError()));
     return AT_OK;
 }
 
@@ -629,6 +639,7 @@ extern "C" int at_localize_host_sharded(at_context **ctxs, int n_ctx, const uint
                                         size_t n_frames, const at_outputs *o)
 {
     if (!ctxs || n_ctx < 1 || !o) return fail(AT_EINVAL, "at_localize_host_sharded: bad argument");
+    int rc_all = AT_OK;
     for (int g = 0; g < n_ctx; g++) {
         at_context *c = ctxs[g];
         const size_t lo = n_frames * g / n_ctx, hi = n_frames * (g + 1) / n_ctx;
@@ -640,14 +651,16 @@ extern "C" int at_localize_host_sharded(at_context **ctxs, int n_ctx, const uint
         OFF(lags, P * 4) OFF(corr, corr_bytes) OFF(raw, P * NL * 8) OFF(cell, 4) OFF(highest, 8) OFF(xy, 8)
         OFF(gate, 1) OFF(classes, (size_t)c->n_cells) OFF(windowed, M * N * 2) OFF(power, M * 8)
 #undef OFF
-        const int rc = host_async(c, h_adc + lo * M * N, h_heads ? h_heads + lo : nullptr, hi - lo, &sub);
-        if (rc != AT_OK) return rc;
+        rc_all = host_async(c, h_adc + lo * M * N, h_heads ? h_heads + lo : nullptr, hi - lo, &sub);
+        if (rc_all != AT_OK) break;
     }
+    // wait for every context touched, also after an error (D2H copies into the caller's arrays may be in flight)
     for (int g = 0; g < n_ctx; g++) {
-        CU(cudaSetDevice(ctxs[g]->cfg.device));
-        for (auto &s : ctxs[g]->slot) CU(cudaStreamSynchronize(s.stream));
+        if (cudaSetDevice(ctxs[g]->cfg.device) != cudaSuccess) continue;
+        for (auto &s : ctxs[g]->slot)
+            if (cudaStreamSynchronize(s.stream) != cudaSuccess && rc_all == AT_OK) rc_all = fail(AT_ECUDA, "at_localize_host_sharded: stream synchronisation failed");
     }
-    return AT_OK;
+    return rc_all;
 }
 
 // ------------------------------------------------------------------ temporal average, likelihood map
@@ -732,7 +745,7 @@ extern "C" int at_gccphat_device(at_context *c, const uint8_t *d_adc, const int3
     if (chunk < 1) chunk = 1;
     if (chunk > n_frames) chunk = n_frames;
     if (c->spec_frames < chunk) {
-        if (c->d_spec) { CU(cudaStreamSynchronize((cudaStream_t)stream)); cudaFree(c->d_spec); c->d_spec = nullptr; }
+        if (c->d_spec) { CU(cudaDeviceSynchronize()); cudaFree(c->d_spec); c->d_spec = nullptr; }   // any stream may still be reading it
         CU(cudaMalloc(&c->d_spec, chunk * per_frame));
         c->spec_frames = chunk;
     }

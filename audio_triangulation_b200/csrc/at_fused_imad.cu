@@ -167,6 +167,13 @@ static cudaError_t launch(const AtFusedParams &p, int sm_count, cudaStream_t st)
 
 } // namespace atk
 
+bool at_fused_imad_supports(const AtShape &sh)
+{   // keep in step with the AT_CASE list below
+    const int m = sh.n_mics, nb = sh.n_bits, l = sh.max_shift;
+    return (m == 3 && nb == 10 && (l == 46 || l == 44)) || (m == 2 && nb == 10 && l == 46) || (m == 8 && (nb == 12 || nb == 10) && l == 46) ||
+           (m == 3 && nb == 12 && l == 46) || (m == 4 && nb == 10 && l == 46);
+}
+
 cudaError_t at_launch_fused_imad(const AtShape &sh, const AtFusedParams &p, int sm_count, cudaStream_t st)
 {
     const bool i16 = p.sig16 != nullptr;

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
                     const int i0 = (j0 - head) & (N - 1);             // chronological index, 16-aligned
                     uint32_t hi[4], lo[4];
                     imma_prep16(rw, mean[ch], s.win2, i0, hi, lo);
+                    AT_CHECK(i0 >= 0 && PAD + i0 + 16 <= PLANE);
                     *reinterpret_cast<uint4 *>(plane(ch, 0) + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4 *>(plane(ch, 1) + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     if (PRUNE && prune) {
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) at_fused_imma_kernel(
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int j = 8 * ((i >> 1) ? row_hi : row_lo) + 2 * t + (i & 1);
+                    AT_CHECK(pr * CSTRIDE + G::NJ <= 3 * CSTRIDE && PAD + 8 * (pr * CSTRIDE + G::NJ) <= 2 * PLANE * 3);   // curve scratch stays inside this warp's planes
                     if (j < G::NJ)
                         curve_base[pr * CSTRIDE + j] = 65536LL * acc[pr][0][i] + 256LL * acc[pr][1][i] + (long long)acc[pr][2][i];
                 }

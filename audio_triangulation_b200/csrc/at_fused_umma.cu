@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
         unsigned pw = 0, v = 0, slot = 0, u = 0, eset = 0;
         for (unsigned i = 0; i < mine; i++) {
             const unsigned pb = pw * G::PBUF + (v & 1), pv = v >> 1;
+            AT_CHECK(pw == i % P && v == i / P && slot == i % G::SLOTS && u == i / G::SLOTS && eset == i % G::SETS);   // incremental counters
             PROF_MARK(0);
             mbar_wait(&s.ready[pb], pv & 1);                        // planes of frame i are in shared memory
             PROF_MARK(1);
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
             const unsigned long long f = frame_of(blockIdx.x + gstride * i);
             PROF_MARK(0);
             const unsigned pb = (unsigned)w * G::PBUF + (n & 1), pv = n >> 1;
+            AT_CHECK(pb < (unsigned)(P * G::PBUF) && mi < (unsigned)G::META);
             uint8_t *const buf = &s.planes[pb][0];
             const uint8_t *const src = &s.rawb[pb][0];
             const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
@@ -426,8 +428,9 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 int (*const ub)[3][128] = s.ubuf[set][par];
 #pragma unroll
                 for (int pr = 0; pr < 3; pr++) {
+                    AT_CHECK(m >= 0 && m < 128 && par < 2 && set < G::SETS);
                     ub[0][pr][m] = u0[pr];
-                    if (wq >= 1 && lane >= 17) ub[1][pr][m - 32] = u1[pr];
+                    if (wq >= 1 && lane >= 17) { AT_CHECK(m - 32 >= 17 && m - 32 < 96); ub[1][pr][m - 32] = u1[pr]; }
                 }
                 const int bar_id = 1 + 2 * set + (int)par;
                 if (p.debug_skip & 16) continue;   // timing experiments: nobody decides

@@ -255,7 +255,10 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
                         int *const zp = &s.z[2 * part + e][0][m + G::PH - 1];
 #pragma unroll
                         for (int ph = 0; ph < G::PH; ph++)  // entry (m, phi): lag index m - phi; |256 a + b| < 2^31
-                            if (m - ph < NJ) zp[ph * G::ZP - ph] = 256 * (int)t[2 * e][ph] + (int)t[2 * e + 1][ph];
+                            if (m - ph < NJ) {
+                                AT_CHECK(m + G::PH - 1 - ph >= 0 && m + G::PH - 1 - ph < G::ZP && 2 * part + e < 8);
+                                zp[ph * G::ZP - ph] = 256 * (int)t[2 * e][ph] + (int)t[2 * e + 1][ph];
+                            }
                     }
                 }
                 named_bar(1, G::EPI_THREADS);
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
 #pragma unroll
                     for (int ph = 0; ph < G::PH; ph++) sum += zr[ph * G::ZP];
                     const unsigned tt = s.couple_tab[g][k];
+                    AT_CHECK((int)(tt >> 8) < NM * (NM - 1) / 2 && j >= 0 && j < NJ && j + G::PH - 1 + (G::PH - 1) * G::ZP < G::PH * G::ZP + G::ZP);
                     long long *const dst = &curvef[(tt >> 8) * NJ + j];
                     if (g == G::PASSES - 1) atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)(sum << (tt & 31)));
                     else *dst += sum << (tt & 31);

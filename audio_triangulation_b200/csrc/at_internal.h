@@ -51,6 +51,7 @@ struct AtShape { int n_mics, n_bits, max_shift; };
 
 // at_fused_imad.cu -- returns cudaErrorInvalidValue for a shape with no instantiation
 cudaError_t at_launch_fused_imad(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
+bool at_fused_imad_supports(const AtShape &shape);
 // at_fused_imma.cu
 cudaError_t at_launch_fused_imma(const AtShape &shape, const AtFusedParams &p, int sm_count, cudaStream_t st);
 bool at_fused_imma_supports(const AtShape &shape);

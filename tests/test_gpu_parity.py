@@ -393,6 +393,8 @@ def test_edge_cases(loc):
         at.Localizer(device=0, n_mics=9)
     with pytest.raises(at.AtError):
         at.Localizer(device=0, max_shift=200)
+    with pytest.raises(at.AtError):                       # in range, but no fused kernel is instantiated for it: refused at create
+        at.Localizer(device=0, n_mics=5)
     before = loc.kernel_launches()
     loc.localize_device(one, want=("lags",))
     # one fused launch per call -- two for the tcgen05 kernel of the reference shape (certified pass + exact pass over its list)
