@@ -181,6 +181,11 @@ class Localizer:
         L.check(self.lib.at_shared_open(self.ctx, bytes(handle), C.byref(ptr)))
         return SharedArray(self, ptr.value, nbytes, bytes(handle), opened=True)
 
+    def copy_async(self, dst, src, nbytes, stream):
+        """Device-to-device copy on a torch stream; dst / src: tensors or DevPtr (e.g. a SharedArray view)."""
+        L.check(self.lib.at_copy_async(self.ctx, C.c_void_p(dst.data_ptr()), C.c_void_p(src.data_ptr()), nbytes,
+                                       C.c_void_p(stream.cuda_stream)))
+
     def peer_enable(self, peer_device):
         """Allow this context's kernels to store into memory of `peer_device` (frame-sharded runs write their results
         straight into rank 0's arrays)."""

@@ -418,6 +418,14 @@ extern "C" int at_shared_close(at_context *c, void *d_ptr, int opened)
     return AT_OK;
 }
 
+extern "C" int at_copy_async(at_context *c, void *d_dst, const void *d_src, size_t bytes, void *stream)
+{
+    if (!c || !d_dst || !d_src) return fail(AT_EINVAL, "at_copy_async: null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return AT_OK;
+}
+
 extern "C" int at_peer_enable(at_context *c, int peer_device)
 {
     if (!c) return fail(AT_EINVAL, "at_peer_enable: null context");

@@ -268,9 +268,10 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
             const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
             mbar_wait(&s.rawfull[pb], pv & 1);          // the frame's bytes are in shared memory
 
-            // channel sums -> floor mean (rolling_buffer.c:48-64); the sum is rotation invariant.  With a 16-aligned head the
-            // lane's ring chunks ARE its chronological chunks (rotated): they stay in registers for the second pass.
-            const bool aligned = (head & 15) == 0;
+            // The lane's chronological chunks [512 q + 16 l, +16) of every channel, un-rotated from the ring (one aligned
+            // 16-byte load, or two and a byte shift when the head is not 16-aligned); they stay in registers for the second
+            // pass.  Channel sums -> floor mean (rolling_buffer.c:48-64).
+            const int uhead = __shfl_sync(0xffffffffu, head, 0);      // tells the compiler what it cannot see: warp-uniform
             uint4 raw[6];
             int mean[3];
             {
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                     sum[ch] = 0;
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
-                        const uint4 x = *reinterpret_cast<const uint4 *>(src + ch * N + ((q * 512 + lane * 16 + (aligned ? head : 0)) & (N - 1)));
+                        const uint4 x = load_chrono16(src + ch * N, q * 512 + lane * 16, uhead);
                         raw[ch * 2 + q] = x;
                         sum[ch] = __dp4a(x.x, 0x01010101u, sum[ch]); sum[ch] = __dp4a(x.y, 0x01010101u, sum[ch]);
                         sum[ch] = __dp4a(x.z, 0x01010101u, sum[ch]); sum[ch] = __dp4a(x.w, 0x01010101u, sum[ch]);
@@ -308,18 +309,10 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 }
             };
             if (!(p.debug_skip & 1)) {
-                if (aligned) {              // the common case, straight-line, from registers
 #pragma unroll
-                    for (int ch = 0; ch < 3; ch++)
+                for (int ch = 0; ch < 3; ch++)
 #pragma unroll
-                        for (int q = 0; q < 2; q++) prep_chunk(ch, q, raw[ch * 2 + q]);
-                } else {
-                    const int uhead = __shfl_sync(0xffffffffu, head, 0);      // tells the compiler what it cannot see: warp-uniform
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++)
-#pragma unroll
-                        for (int q = 0; q < 2; q++) prep_chunk(ch, q, load_chrono16(src + ch * N, q * 512 + lane * 16, uhead));
-                }
+                    for (int q = 0; q < 2; q++) prep_chunk(ch, q, raw[ch * 2 + q]);
             }
             if constexpr (CERT) {
 #pragma unroll

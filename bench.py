@@ -188,18 +188,41 @@ def run_ours(args):
         for k, (_, _, bpf) in shapes.items():          # [lags of all ranks][cell of all ranks][xy of all ranks]
             off[k] = base
             base += world * F * bpf
-        out = {k: shared.view(off[k] + rank * F * bpf, F * bpf) for k, (_, _, bpf) in shapes.items()}
+        remote = {k: shared.view(off[k] + rank * F * bpf, F * bpf) for k, (_, _, bpf) in shapes.items()}
+        out = remote
         if rank == 0:
             whole = shared.tensor()
             glob = {k: whole[off[k]: off[k] + world * F * bpf].view(d).view((world,) + sh) for k, (sh, d, bpf) in shapes.items()}
             out = {k: glob[k][0] for k in shapes}
     else:
         out = {k: torch.empty(sh, dtype=d, device=dev) for k, (sh, d, _) in shapes.items()}
+    # --gather copy: the kernel stores into local double buffers and a side stream moves each step's 24 MB slice to rank 0
+    # with the copy engine while the next step computes (no small store packets on NVLink)
+    staged = world > 1 and rank != 0 and args.gather == "copy"
+    if staged:
+        bufs = [{k: torch.empty(sh, dtype=d, device=dev) for k, (sh, d, _) in shapes.items()} for _ in range(2)]
+        side = torch.cuda.Stream(dev)
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+    nstep = [0]
 
     def step():
-        loc.localize_device(adc, None, want=WANT, out=out)
+        if not staged:
+            loc.localize_device(adc, None, want=WANT, out=out)
+            return
+        b = nstep[0] & 1
+        nstep[0] += 1
+        stream.wait_event(done[b])                      # the copy that last read this buffer
+        loc.localize_device(adc, None, want=WANT, out=bufs[b])
+        ready = torch.cuda.Event()
+        ready.record(stream)
+        side.wait_event(ready)
+        for k, (_, _, bpf) in shapes.items():
+            loc.copy_async(remote[k], bufs[b][k], F * bpf, side)
+        done[b].record(side)
 
     def barrier():
+        if staged:
+            stream.wait_stream(side)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -215,13 +238,22 @@ def run_ours(args):
     ev0.record(stream)
     for _ in range(args.steps):
         step()
+    if staged:
+        stream.wait_stream(side)                        # the last slice has arrived at rank 0 inside the timed region
     ev1.record(stream)
     barrier()
     launches = loc.kernel_launches() - launches0
     clocks = sampler.finish()
     total_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([total_ms / args.steps, clocks["sm_mhz"] or 0.0, float("sw_power_cap" in clocks["reasons"])],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(x[0].item(), 4) for x in allr], "sm_mhz": [x[1].item() for x in allr],
+                    "sw_power_cap": [bool(x[2].item()) for x in allr]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = t.item()
     kern_ms = total_ms / args.steps          # the step IS the kernel (certified pass + exact pass over its short list)
@@ -389,8 +421,10 @@ def run_ours(args):
                 "dtype": "int16 x int16 -> int64, computed as 4 x (int8 x int8 -> int32) on tensor cores (u8 ADC in)", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "frames_per_gpu": F, "global_frames": world * F,
                            "kernel": args.kernel, "likelihood_search": search, "l2": "inputs (3.2 GB/GPU) larger than L2, no flush",
-                           "sharding": ("contiguous frame ranges; every rank's kernel stores its 24 B/frame straight into rank 0's "
-                                        "arrays (CUDA-IPC peer memory over NVLink)") if world > 1 else "single GPU"},
+                           "sharding": (("contiguous frame ranges; every rank's kernel stores its 24 B/frame straight into rank 0's "
+                                         "arrays (CUDA-IPC peer memory over NVLink)") if args.gather == "stores" else
+                                        ("contiguous frame ranges; every rank's 24 B/frame go to rank 0's arrays (CUDA-IPC peer memory) "
+                                         "by copy-engine peer copies overlapped with the next step")) if world > 1 else "single GPU"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * BYTES_IN_PER_FRAME,
                         "d2h_bytes_per_step": F * BYTES_OUT_PER_FRAME, "steps": e2e_steps, "matches_device_path": e2e_ok,
@@ -398,6 +432,7 @@ def run_ours(args):
                 "roofline": roof}
         if world > 1:
             line["sharded_bytes_identical"] = sharded_ok
+            line["per_rank"] = per_rank
         line.update(extra)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's own objects on the host cores
@@ -459,6 +494,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--gather", default="stores", choices=["stores", "copy"],
+                    help="N > 1: kernels store results straight into rank 0's arrays, or local buffers + copy-engine peer copies")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

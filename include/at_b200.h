@@ -219,6 +219,8 @@ int at_shared_alloc(at_context *ctx, size_t bytes, void **d_ptr, at_ipc_handle *
 int at_shared_open(at_context *ctx, const at_ipc_handle *handle, void **d_ptr);
 int at_shared_close(at_context *ctx, void *d_ptr, int opened /* 1: from at_shared_open, 0: from at_shared_alloc */);
 int at_peer_enable(at_context *ctx, int peer_device);
+/* Asynchronous device-to-device copy on `stream` (copy engine; either pointer may be an at_shared_open mapping). */
+int at_copy_async(at_context *ctx, void *d_dst, const void *d_src, size_t bytes, void *stream);
 
 /* Temporal stage for `n_arrays` independent arrays (ref: sample_compute.h:124-139,
  * correlations.c:38-63): where gate[i] != 0, estimate <- EMA(estimate, fresh) with the array's own
