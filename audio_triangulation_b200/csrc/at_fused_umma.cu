@@ -75,15 +75,23 @@ struct UmmaGeo {
     static constexpr int FRAME = NPLANES * PLANE;       // 6 912 bytes of planes per frame
     static constexpr int NJ = 96;                       // lag slots kept (j = 0..95), j in [PAD-L, PAD+L] are real
     static constexpr int NL = 2 * L + 1;
-    static constexpr int TCOLS = CERT ? 128 : 160;      // TMEM columns per accumulator slot (96 / 144 used)
+    static constexpr int TCOLS = CERT ? 96 : 160;       // TMEM columns per accumulator slot (96 / 144 used)
     // Accumulator slots in TMEM.  Their number must not divide SETS: frame i then re-uses the slot of frame i - SLOTS, which
-    // another epilogue set has drained, and the tensor core can work one frame ahead of every set.
-    static constexpr int SLOTS = CERT ? 4 : 3;
-    static constexpr int PREP_WARPS = 7, PBUF = 2, SETS = 5, META = 32;
+    // another epilogue set has drained, and the tensor core can work one frame ahead of every set.  It must not exceed SETS
+    // either: the next frame of a set (i + SETS) then cannot complete before every warp of the set has released frame i, so
+    // a set's `full` barrier is never two phases ahead of a waiting warp (a parity wait could not tell).
+#ifndef AT_UMMA_SETS
+#define AT_UMMA_SETS 5
+#endif
+#ifndef AT_UMMA_PREP
+#define AT_UMMA_PREP 7
+#endif
+    static constexpr int PREP_WARPS = AT_UMMA_PREP, PBUF = 2, SETS = AT_UMMA_SETS, META = 32;
+    static constexpr int SLOTS = CERT ? (SETS % 4 != 0 ? 4 : 3) : 3;
     static constexpr int THREADS = 32 * (1 + PREP_WARPS + 4 * SETS);
     static_assert(PAD >= L && PAD + L + 15 < 128 && PAD + L < NJ, "lag window must fit the 128-row tile");
     static_assert(127 + 16 * 63 + 16 <= PLANE, "A operand reads stay inside a plane buffer");
-    static_assert(SLOTS * TCOLS <= 512 && SETS % SLOTS != 0, "TMEM columns / slot rotation");
+    static_assert(SLOTS * TCOLS <= 512 && SETS % SLOTS != 0 && SLOTS <= SETS, "TMEM columns / slot rotation");
     static constexpr int PREP0 = 4 * SETS, MMAW = PREP0 + PREP_WARPS;   // first prep warp, MMA warp (epilogue warp w owns TMEM lane quarter w % 4)
     static_assert(META >= PREP_WARPS * PBUF + SLOTS + SETS, "meta ring must outlive every frame in flight");
     // first TMEM column (within a slot) of the hh (0) / mid (1) / ll (2) tile of pair 0 = (a,b), 1 = (a,c), 2 = (b,c)
@@ -409,8 +417,8 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
 #pragma unroll
                         for (int pr = 0; pr < 3; pr++) { u0[pr] = a1.v[pr] ^ a2.v[pr + 3] ^ a0.v[pr + 6]; u1[pr] = a1.v[pr + 9] + a2.v[pr + 12] + a0.v[15 - pr]; }
                     } else {
+                        diag_butterfly(a0, lane, u0[0], u1[0]);          // the single one first: fewest registers live at the peak
                         diag_butterfly2(a1, a2, lane, u0[1], u1[1], u0[2], u1[2]);
-                        diag_butterfly(a0, lane, u0[0], u1[0]);
                     }
                 }
                 PROF_MARK(2);

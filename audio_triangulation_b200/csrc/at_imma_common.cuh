@@ -148,8 +148,10 @@ __device__ __forceinline__ bool peak_tuple_lookup(const AtFusedParams &p, unsign
 
 // Warp-scope epilogue for the optional products; curve[][] holds raw sums indexed by j = s + PAD,
 // b0..b2 are the three best shifts (warp-uniform).
-template <int L, int PAD, int NJ, int CSTRIDE>
-__device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, int b1s, int b2s, const float *gauss_s,
+// FULL_SCAN = false: when neither the tuple look-up nor a bounded box settles the likelihood maximum the function stores
+// nothing for cell / highest / xy and returns false -- the caller then scans all tuples with more threads (gate is written).
+template <int L, int PAD, int NJ, int CSTRIDE, bool FULL_SCAN = true>
+__device__ __forceinline__ bool epilogue_warp(long long *curve_base, int b0s, int b1s, int b2s, const float *gauss_s,
                                               const AtFusedParams &p, unsigned long long f, int lane)
 {
     constexpr int P = 3, NL = 2 * L + 1, OFF = PAD - L;
@@ -162,7 +164,7 @@ __device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, in
     }
     if (p.raw)
         for (int idx = lane; idx < P * NL; idx += 32) p.raw[f * (unsigned long long)(P * NL) + idx] = CURVE(idx / NL, OFF + idx % NL);
-    if (!(p.corr || p.cell || p.highest || p.xy || p.classes)) return;
+    if (!(p.corr || p.cell || p.highest || p.xy || p.classes)) return true;
     // Gaussian re-weighting (correlations.c:26-33): in place when whole curves are wanted, otherwise
     // evaluated on demand for the few entries the bounded likelihood search touches.
     const bool weighted = p.corr || p.classes;
@@ -195,7 +197,7 @@ __device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, in
             for (int idx = lane; idx < P * NL; idx += 32) base[idx] = CURVE(idx / NL, OFF + idx % NL);
         }
     }
-    if (!(p.cell || p.highest || p.xy || p.classes)) return;
+    if (!(p.cell || p.highest || p.xy || p.classes)) return true;
     // vga_heatmap.h:96-108: maximum of L = sum_pairs CURVE(pair, lut) over the distinct LUT tuples,
     // first row-major cell on ties.  Exact bounded search: every entry of curve p is <= Pmax_p =
     // max(CURVE(p, best_p), 0), and an entry at distance >= r from the peak is <= trunc(peak * g[r])
@@ -256,6 +258,7 @@ __device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, in
             b = scan_box(R_FIRST, R_FIRST);
             ok = b.v > bound(pk0, R_FIRST + 1) + others0 && b.v > bound(pk1, R_FIRST + 1) + others1;
         }
+        if (!ok && !FULL_SCAN) return false;     // the caller scans with more threads than this warp has
         if (!ok && b.v != LLONG_MIN) {          // widen: smallest radii whose outside bound is below what we hold
             int r0 = -1, r1 = -1;
             for (int r = R_FIRST; r <= R_MAX && (r0 < 0 || r1 < 0); r++) {
@@ -294,6 +297,7 @@ __device__ __forceinline__ void epilogue_warp(long long *curve_base, int b0s, in
             p.classes[f * (unsigned long long)p.n_cells + c] = like >= tw ? 15 : like >= tg ? 3 : like >= tr ? 8 : like >= tb ? 5 : 0;
         }
     }
+    return true;
 }
 #undef CURVE
 
