@@ -247,13 +247,14 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
     } else if (warp >= G::PREP0) {
         // =================================================================== prep warps
         const int w = warp - G::PREP0;
-        // Lane l owns the chronological samples [512 q + 16 l, +16) of every channel and frame: its slice of the doubled
+        // Lane l owns the chronological samples [16 l, +16) and their mirror image of every channel and frame: its slice of the doubled
         // window, pre-masked for IDP.2A (even samples in the low half, odd samples in the high half), lives in registers.
-        uint32_t wr[2][16];
+        // Its second chunk is the MIRROR of the first, [N - 16 - 16 l, +16): the window is symmetric, so the same 16 registers
+        // serve both (umma_prep16m).
+        uint32_t wr[16];
 #pragma unroll
-        for (int q = 0; q < 2; q++)
-#pragma unroll
-            for (int e = 0; e < 16; e++) wr[q][e] = (uint32_t)(2 * (int)p.window[q * 512 + lane * 16 + e]) << ((e & 1) * 16);
+        for (int e = 0; e < 16; e++) wr[e] = (uint32_t)(2 * (int)p.window[lane * 16 + e]) << ((e & 1) * 16);
+        auto chunk_at = [&](int q) { return q == 0 ? lane * 16 : N - 16 - lane * 16; };
         PROF_DECL;
         // Raw frames arrive by 1-D bulk copies (TMA) into this warp's two staging buffers, one frame ahead: lane 0 starts
         // the copy of frame i + P as soon as the buffer's previous frame has been consumed.
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                     sum[ch] = 0;
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
-                        const uint4 x = load_chrono16(src + ch * N, q * 512 + lane * 16, uhead);
+                        const uint4 x = load_chrono16(src + ch * N, chunk_at(q), uhead);
                         raw[ch * 2 + q] = x;
                         sum[ch] = __dp4a(x.x, 0x01010101u, sum[ch]); sum[ch] = __dp4a(x.y, 0x01010101u, sum[ch]);
                         sum[ch] = __dp4a(x.z, 0x01010101u, sum[ch]); sum[ch] = __dp4a(x.w, 0x01010101u, sum[ch]);
@@ -304,10 +305,11 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
             PROF_MARK(2);
             unsigned sl[3] = {0, 0, 0};
             auto prep_chunk = [&](int ch, int q, const uint4 x) {
-                const int i0 = q * 512 + lane * 16;
+                const int i0 = chunk_at(q);
                 const uint32_t rw[4] = {x.x, x.y, x.z, x.w};
                 uint32_t hi[4], lo[4];
-                umma_prep16r(rw, mean[ch], wr[q], hi, lo);
+                if (q == 0) umma_prep16r(rw, mean[ch], wr, hi, lo);
+                else umma_prep16m(rw, mean[ch], wr, hi, lo);
                 AT_CHECK(umma_plane(ch, 1) * PLANE + PAD + i0 + 16 <= G::FRAME);
                 *reinterpret_cast<uint4 *>(buf + umma_plane(ch, 0) * PLANE + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(buf + umma_plane(ch, 1) * PLANE + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -400,13 +402,19 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 {
                     // all six tiles leave TMEM before the first butterfly, so that the slot goes back to the tensor core early
                     Arr<16> a1, a2, a0;
-                    {
-                        uint32_t h[16], md[16], h2[16], md2[16];
+                    {   // one pair at a time: 32 registers in flight next to the packed arrays (no spills); the two extra TMEM
+                        // round trips are covered by the other sets
+                        uint32_t h[16], md[16];
                         tmem_ld16(ta + G::col(1, 0), h); tmem_ld16(ta + G::col(1, 1), md);
-                        tmem_ld16(ta + G::col(2, 0), h2); tmem_ld16(ta + G::col(2, 1), md2);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; j++) { a1.v[j] = (int)h[j] * 256 + (int)md[j]; a2.v[j] = (int)h2[j] * 256 + (int)md2[j]; }
+                        for (int j = 0; j < 16; j++) a1.v[j] = (int)h[j] * 256 + (int)md[j];
+                        asm volatile("" :: "r"(a1.v[0]), "r"(a1.v[5]), "r"(a1.v[10]), "r"(a1.v[15]));   // pack before the next loads are issued
+                        tmem_ld16(ta + G::col(2, 0), h); tmem_ld16(ta + G::col(2, 1), md);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) a2.v[j] = (int)h[j] * 256 + (int)md[j];
+                        asm volatile("" :: "r"(a2.v[0]), "r"(a2.v[5]), "r"(a2.v[10]), "r"(a2.v[15]));
                         tmem_ld16(ta + G::col(0, 0), h); tmem_ld16(ta + G::col(0, 1), md);
                         tmem_ld_wait();
                         release_slot();
@@ -562,9 +570,12 @@ bool at_fused_umma_supports(const AtShape &sh)
     return sh.n_mics == 3 && sh.n_bits == 10 && (sh.max_shift == 46 || sh.max_shift == 44);
 }
 
-// |256 hh + mid| must fit an int32 for every possible frame: |h| <= hmax_i = ((W_i + 128) >> 8) + 1, |l| <= 128
+// |256 hh + mid| must fit an int32 for every possible frame: |h| <= hmax_i = ((W_i + 128) >> 8) + 1, |l| <= 128;
+// and the window must be symmetric (the prep warps keep half of it in registers)
 bool at_fused_umma_window_ok(const int16_t *window, int n)
 {
+    for (int i = 0; i < n / 2; i++)
+        if (window[i] != window[n - 1 - i]) return false;
     long long s2 = 0, s1 = 0;
     for (int i = 0; i < n; i++) { const long long h = (((long long)window[i] + 128) >> 8) + 1; s2 += h * h; s1 += h; }
     return 256 * s2 + 2 * 128 * s1 < (1ll << 31);

@@ -113,6 +113,26 @@ __device__ __forceinline__ void umma_prep16r(const uint32_t (&rw)[4], int mean, 
         hi[w4] = __byte_perm(t01, t23, 0x7632);
     }
 }
+// The mirrored chunk: the window is symmetric (W[i] == W[N-1-i]), so sample e of the chunk that mirrors the lane's first one
+// uses the window word of sample 15 - e -- whose parity, hence pre-masked half, is the other one.  Swapping the bytes of
+// each data half-word (one PRMT per word) puts the byte under the half that holds the window: 16 window registers serve
+// both chunks.
+__device__ __forceinline__ void umma_prep16m(const uint32_t (&rw)[4], int mean, const uint32_t (&wr)[16],
+                                             uint32_t (&hi)[4], uint32_t (&lo)[4])
+{
+    const uint32_t k4 = (uint32_t)((256 - mean) & 0xFF) * 0x01010101u;
+    const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
+#pragma unroll
+    for (int w4 = 0; w4 < 4; w4++) {
+        const uint32_t d0 = sub_bytes(rw[w4], k7, kM), d = __byte_perm(d0, d0, 0x2301);
+        const int p0 = dp2a_lo_acc(wr[15 - 4 * w4], d, 0x8000), p1 = dp2a_lo_acc(wr[14 - 4 * w4], d, 0x8000);
+        const int p2 = dp2a_hi_acc(wr[13 - 4 * w4], d, 0x8000), p3 = dp2a_hi_acc(wr[12 - 4 * w4], d, 0x8000);
+        const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
+        const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
+        lo[w4] = __byte_perm(t01, t23, 0x5410) ^ 0x80808080u;
+        hi[w4] = __byte_perm(t01, t23, 0x7632);
+    }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
