@@ -93,7 +93,8 @@ struct UmmaGeo {
     static_assert(127 + 16 * 63 + 16 <= PLANE, "A operand reads stay inside a plane buffer");
     static_assert(SLOTS * TCOLS <= 512 && SETS % SLOTS != 0 && SLOTS <= SETS, "TMEM columns / slot rotation");
     static constexpr int PREP0 = 4 * SETS, MMAW = PREP0 + PREP_WARPS;   // first prep warp, MMA warp (epilogue warp w owns TMEM lane quarter w % 4)
-    static_assert(META >= PREP_WARPS * PBUF + SLOTS + SETS, "meta ring must outlive every frame in flight");
+    static_assert(META >= PREP_WARPS * PBUF + SLOTS + 2 * SETS, "meta ring must outlive every frame in flight (decisions lag one frame)");
+    static_assert(!CERT || 3 * SETS <= 15, "one named barrier per set and exchange buffer");
     // first TMEM column (within a slot) of the hh (0) / mid (1) / ll (2) tile of pair 0 = (a,b), 1 = (a,c), 2 = (b,c)
     __host__ __device__ static constexpr int col(int pr, int cls)
     {
@@ -109,9 +110,9 @@ struct UmmaSmem {
     using G = UmmaGeo<L, CERT>;
     alignas(128) uint8_t planes[G::PREP_WARPS * G::PBUF][G::FRAME];
     alignas(128) uint8_t rawb[G::PREP_WARPS * G::PBUF][3 * G::N];   // ring-ordered ADC bytes, staged by bulk copies (TMA)
-    // CERT: diagonal sums of the three pairs by lag index, [set][frame parity][n0 | n1][pair][lag index]; the n1 entries no
+    // CERT: diagonal sums of the three pairs by lag index, [set][frame mod 3][n0 | n1][pair][lag index]; the n1 entries no
     // quarter ever writes stay zero from the kernel's start
-    alignas(16) int ubuf[CERT ? G::SETS : 1][2][2][3][128];
+    alignas(16) int ubuf[CERT ? G::SETS : 1][3][2][3][128];
     alignas(16) int4 ptab[4 * G::SETS];                  // CERT: per epilogue warp, the peak-tuple table entry of its last certified frame (cp.async)
     // exact variant
     alignas(16) EpiSmem<3, 10, L> epi[CERT ? 1 : G::SETS];       // raw curves by lag index + scratch of the group epilogue
@@ -378,9 +379,60 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 }
             }
         };
+        // CERT: the decision of frame n_d of this set (exchange buffer kb_d = n_d % 3), by the warp whose turn it is
+        auto decide = [&](unsigned n_d, unsigned kb_d) {
+            if constexpr (CERT) {
+                named_bar(1 + 3 * set + (int)kb_d, 128);       // completes at once: the other quarters arrived a frame ago
+                flush_pending();
+                const unsigned i_d = (unsigned)set + (unsigned)G::SETS * n_d;
+                const unsigned long long f = frame_of(blockIdx.x + gstride * i_d);
+                const uint32_t *const sl = s.meta[i_d % G::META];
+                int (*const ub)[3][128] = s.ubuf[set][kb_d];
+                bool sure = true;
+                int b3[3];
+#pragma unroll
+                for (int pr = 0; pr < 3; pr++) {
+                    // lane holds lag indices j = lane, lane + 32, lane + 64 (ascending): U[j] = n0[j] + n1[j]
+                    int v[3];
+#pragma unroll
+                    for (int t = 0; t < 3; t++) {
+                        const int j = lane + 32 * t;
+                        v[t] = (j >= PAD - L && j <= PAD + L) ? ub[0][pr][j] + ub[1][pr][j] : INT_MIN;
+                    }
+                    // first-max arg-max (correlations.c:20-23 on C9 = 256 U) and the runner-up
+                    const int top_l = max(v[0], max(v[1], v[2]));
+                    const int j_l = v[0] == top_l ? lane : (v[1] == top_l ? lane + 32 : lane + 64);
+                    const int top = __reduce_max_sync(0xffffffffu, top_l);
+                    const int j1 = __reduce_min_sync(0xffffffffu, top_l == top ? j_l : 0x7fffffff);
+                    const int sec_l = max(j1 == lane ? INT_MIN : v[0], max(j1 == lane + 32 ? INT_MIN : v[1], j1 == lane + 64 ? INT_MIN : v[2]));
+                    const int second = __reduce_max_sync(0xffffffffu, sec_l);
+                    // |ll| <= B = sqrt(Sl_x Sl_y) (rounded up, < 2^25): the arg-max is certain when 256 (top - second) > 2 B
+                    // and the exact peak 256 top - B >= 2048; both tested a little conservatively in 32-bit arithmetic
+                    const int xc = pr == 2 ? 1 : 0, yc = pr == 0 ? 1 : 2;
+                    const unsigned bnd = (unsigned)sqrt_prod_up(sl[xc], sl[yc]) + 1u;
+                    sure = sure && (unsigned)(top - second) > (bnd >> 7) + 1u && top > (int)((bnd + 2048u) >> 8) + 1;
+                    b3[pr] = j1 - PAD;
+                }
+                if (sure) {
+                    // certified lags are final; the position comes from the peak-tuple table
+                    if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? b3[0] : (lane == 1 ? b3[1] : b3[2]);
+                    if (lane == 0 && p.gate) p.gate[f] = (b3[0] * b3[0] + b3[1] * b3[1] + b3[2] * b3[2]) > 4 ? 1 : 0;   // sample_compute.h:124-134
+                    if (wants_pos) {
+                        if (lane == 0) {
+                            const int idx = ((b3[0] + L) * (2 * L + 1) + (b3[1] + L)) * (2 * L + 1) + (b3[2] + L);
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(&s.ptab[warp])), "l"(p.peak_tab + idx) : "memory");
+                        }
+                        pend_f = f; pend = true;
+                    } else if (lane == 0 && p.stats) atomicAdd(&p.stats[4], 1ull);
+                } else if (lane == 0) {
+                    p.redo_list[atomicAdd(p.redo_count, 1u)] = (uint32_t)f;      // the exact variant finishes this frame
+                }
+            }
+        };
         PROF_DECL;
         unsigned slot = (unsigned)set % G::SLOTS, mi = (unsigned)set % G::META;   // i % SLOTS, i % META, kept incrementally
-        for (unsigned n = 0, i = (unsigned)set; i < mine; n++, i += G::SETS, par ^= 1,
+        unsigned kb = 0;      // n % 3
+        for (unsigned n = 0, i = (unsigned)set; i < mine; n++, i += G::SETS, par ^= 1, kb = kb == 2 ? 0 : kb + 1,
                       slot = (slot + G::SETS) % G::SLOTS, mi = mi + G::SETS >= G::META ? mi + G::SETS - G::META : mi + G::SETS) {
             const unsigned long long k = blockIdx.x + gstride * i;
             PROF_MARK(0);
@@ -434,61 +486,20 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 // quarter) and, lanes >= 17, n1 = the part of lag index m - 32 that this quarter's rows hold.  One warp per
                 // frame -- the role rotates over the four quarters -- adds the two, finds the arg-max and decides; the other
                 // three arrive on the barrier and go on to their next frame.
-                int (*const ub)[3][128] = s.ubuf[set][par];
+                int (*const ub)[3][128] = s.ubuf[set][kb];
 #pragma unroll
                 for (int pr = 0; pr < 3; pr++) {
-                    AT_CHECK(m >= 0 && m < 128 && par < 2 && set < G::SETS);
+                    AT_CHECK(m >= 0 && m < 128 && kb < 3 && set < G::SETS);
                     ub[0][pr][m] = u0[pr];
                     if (wq >= 1 && lane >= 17) { AT_CHECK(m - 32 >= 17 && m - 32 < 96); ub[1][pr][m - 32] = u1[pr]; }
                 }
-                const int bar_id = 1 + 2 * set + (int)par;
                 if (p.debug_skip & 16) continue;   // timing experiments: nobody decides
-                if (wq != (int)(n & 3)) { named_bar_arrive(bar_id, 128); continue; }   // (bar.arrive orders the stores above: PTX producer / consumer pattern)
-                named_bar(bar_id, 128);
+                // (bar.arrive orders the stores above: PTX producer / consumer pattern.)  The deciding warp of this frame does
+                // not stop here either: it synchronises and decides one frame later, after its own work on the next frame, when
+                // the other three have long arrived -- no warp ever waits for a decision.
+                if (wq != (int)(n & 3)) named_bar_arrive(1 + 3 * set + (int)kb, 128);
                 PROF_MARK(3);
-                flush_pending();
-                const unsigned long long f = frame_of(k);
-                const uint32_t *const sl = s.meta[mi];
-                bool sure = true;
-                int b3[3];
-#pragma unroll
-                for (int pr = 0; pr < 3; pr++) {
-                    // lane holds lag indices j = lane, lane + 32, lane + 64 (ascending): U[j] = n0[j] + n1[j]
-                    int v[3];
-#pragma unroll
-                    for (int t = 0; t < 3; t++) {
-                        const int j = lane + 32 * t;
-                        v[t] = (j >= PAD - L && j <= PAD + L) ? ub[0][pr][j] + ub[1][pr][j] : INT_MIN;
-                    }
-                    // first-max arg-max (correlations.c:20-23 on C9 = 256 U) and the runner-up
-                    const int top_l = max(v[0], max(v[1], v[2]));
-                    const int j_l = v[0] == top_l ? lane : (v[1] == top_l ? lane + 32 : lane + 64);
-                    const int top = __reduce_max_sync(0xffffffffu, top_l);
-                    const int j1 = __reduce_min_sync(0xffffffffu, top_l == top ? j_l : 0x7fffffff);
-                    const int sec_l = max(j1 == lane ? INT_MIN : v[0], max(j1 == lane + 32 ? INT_MIN : v[1], j1 == lane + 64 ? INT_MIN : v[2]));
-                    const int second = __reduce_max_sync(0xffffffffu, sec_l);
-                    // |ll| <= B = sqrt(Sl_x Sl_y) (rounded up, < 2^25): the arg-max is certain when 256 (top - second) > 2 B
-                    // and the exact peak 256 top - B >= 2048; both tested a little conservatively in 32-bit arithmetic
-                    const int xc = pr == 2 ? 1 : 0, yc = pr == 0 ? 1 : 2;
-                    const unsigned bnd = (unsigned)sqrt_prod_up(sl[xc], sl[yc]) + 1u;
-                    sure = sure && (unsigned)(top - second) > (bnd >> 7) + 1u && top > (int)((bnd + 2048u) >> 8) + 1;
-                    b3[pr] = j1 - PAD;
-                }
-                PROF_MARK(4);
-                if (sure) {
-                    // certified lags are final; the position comes from the peak-tuple table
-                    if (lane < 3 && p.lags) p.lags[f * 3 + lane] = lane == 0 ? b3[0] : (lane == 1 ? b3[1] : b3[2]);
-                    if (lane == 0 && p.gate) p.gate[f] = (b3[0] * b3[0] + b3[1] * b3[1] + b3[2] * b3[2]) > 4 ? 1 : 0;   // sample_compute.h:124-134
-                    if (wants_pos) {
-                        if (lane == 0) {
-                            const int idx = ((b3[0] + L) * (2 * L + 1) + (b3[1] + L)) * (2 * L + 1) + (b3[2] + L);
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(&s.ptab[warp])), "l"(p.peak_tab + idx) : "memory");
-                        }
-                        pend_f = f; pend = true;
-                    } else if (lane == 0 && p.stats) atomicAdd(&p.stats[4], 1ull);
-                } else if (lane == 0) {
-                    p.redo_list[atomicAdd(p.redo_count, 1u)] = (uint32_t)f;      // the exact variant finishes this frame
-                }
+                if (n >= 1 && wq == (int)((n - 1) & 3)) decide(n - 1, kb == 0 ? 2u : kb - 1);
                 PROF_MARK(6);
             } else {
                 // ---- exact variant: U = 256 hh + mid and ll of the three pairs; corr = 256 U + ll
@@ -555,7 +566,12 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                 PROF_MARK(6);
             }
         }
-        if constexpr (CERT) flush_pending();
+        if constexpr (CERT) {
+            // the set's last frame has not been decided yet
+            const unsigned cnt = mine > (unsigned)set ? (mine - (unsigned)set + G::SETS - 1) / G::SETS : 0u;
+            if (cnt >= 1 && !(p.debug_skip & (4 | 16)) && wq == (int)((cnt - 1) & 3)) decide(cnt - 1, (cnt - 1) % 3);
+            flush_pending();
+        }
         PROF_FLUSH(2 + (wq == 0 ? 0 : 1));
     }
     tc_fence_before();
