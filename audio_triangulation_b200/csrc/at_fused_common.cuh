@@ -65,6 +65,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
 }
+// Wait of a warp that has slack: one probe, then fixed naps between probes.  A try_wait with a suspend hint compiles to
+// NANOSLEEP.SYNCS, which wakes on every mbarrier event of the CTA -- with a dozen waiting warps and twenty events per frame
+// that is ~200 wake-ups (each two shared-memory probes) per frame; a plain nap costs a little wake-up latency instead.
+#ifndef AT_WAIT_NS
+#define AT_WAIT_NS 100
+#endif
+__device__ __forceinline__ void mbar_wait_slack(uint64_t *bar, uint32_t parity)
+{
+#if AT_WAIT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "NAP_%=:\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra NAP_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)AT_WAIT_NS) : "memory");
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {

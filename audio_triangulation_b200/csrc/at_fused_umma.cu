@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
             uint8_t *const buf = &s.planes[pb][0];
             const uint8_t *const src = &s.rawb[pb][0];
             const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
-            mbar_wait(&s.rawfull[pb], pv & 1);          // the frame's bytes are in shared memory
+            mbar_wait_slack(&s.rawfull[pb], pv & 1);         // the frame's bytes are in shared memory
 
             // The lane's chronological chunks [512 q + 16 l, +16) of every channel, un-rotated from the ring (one aligned
             // 16-byte load, or two and a byte shift when the head is not 16-aligned); they stay in registers for the second
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
             }
             PROF_MARK(1);
             // the tensor core must be done with the frame that used this plane buffer before
-            if (pv >= 1) mbar_wait(&s.sfree[pb], (pv - 1) & 1);
+            if (pv >= 1) mbar_wait_slack(&s.sfree[pb], (pv - 1) & 1);
             PROF_MARK(2);
             unsigned sl[3] = {0, 0, 0};
             auto prep_chunk = [&](int ch, int q, const uint4 x) {
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                       slot = (slot + G::SETS) % G::SLOTS, mi = mi + G::SETS >= G::META ? mi + G::SETS - G::META : mi + G::SETS) {
             const unsigned long long k = blockIdx.x + gstride * i;
             PROF_MARK(0);
-            mbar_wait(&s.full[set], n & 1);             // full[] is per set (waited in order by that set), empty[] per slot
+            mbar_wait_slack(&s.full[set], n & 1);            // full[] is per set (waited in order by that set), empty[] per slot
             PROF_MARK(1);
             tc_fence_after();
             auto release_slot = [&]() {   // this warp's accumulators are out of TMEM: hand the slot back to the tensor core
