@@ -415,6 +415,21 @@ def run_ours(args):
                 "hbm_achieved_gbs": hbm_ach, "hbm_peak_gbs": hbm_peak, "hbm_frac": hbm_ach / hbm_peak,
                 "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
                 "microbench_gops": ubench}
+        # the north-star's other denominators: the integer pipe (one IMAD = one int16 MAC) -- what the best CUDA-core
+        # kernel could reach -- and, from the committed ncu capture, the pipe that actually bounds the tcgen05 kernel
+        if ubench.get("imad"):
+            roof["int_pipe_peak_tmac_per_s"] = ubench["imad"] / 1e3
+            roof["frac_of_int_pipe_roofline"] = roof["int16_tmac_per_s"] / (ubench["imad"] / 1e3)
+        if tc:
+            try:
+                cap = json.load(open(os.path.join(ROOT, "profiles", "r2_umma_full.json")))[0]
+                tcw = cap["l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]["value"]
+                lsw = cap["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]["value"]
+                roof["limiter"] = {"pipe": "shared-memory data pipe (tensor-core operand fetch + LSU)", "busy_frac": (tcw + lsw) / 100.0,
+                                   "tensor_operand_fetch_frac": tcw / 100.0, "lsu_frac": lsw / 100.0,
+                                   "source": "profiles/r2_umma_full.json (ncu --set full of this kernel, not measured in this run)"}
+            except Exception:
+                pass
         line = {"metric": "localized frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
