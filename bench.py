@@ -312,6 +312,21 @@ def run_ours(args):
     if rank == 0:
         e2e_ok = all(bool((hout[k].numpy() == out[k].cpu().numpy()).all()) for k in WANT)
     h2d_gbs = world * F * BYTES_IN_PER_FRAME * e2e_steps / te.item() / 1e9
+    # the same with the reference's complete per-frame product out: whole correlations_t structs (post-Gaussian curves,
+    # lags, time stamp; 2 280 B/frame D2H next to the 3 072 B/frame H2D) -- what the reference arm computes per frame
+    e2e_struct = None
+    if world == 1 and not args.no_extras:
+        Fs = min(F, 1 << 18)
+        hs = {"lags": torch.empty((Fs, 3), dtype=torch.int32).pin_memory(),
+              "corr": torch.empty((Fs, 3, 95), dtype=torch.int64).pin_memory()}
+        loc.localize_host(pinned[:Fs], want=("lags", "corr"), out=hs, struct_corr=True)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            loc.localize_host(pinned[:Fs], want=("lags", "corr"), out=hs, struct_corr=True)
+        dt = time.perf_counter() - t0
+        e2e_struct = {"value": Fs * 3 / dt, "unit": "frames/s", "frames": Fs, "h2d_bytes_per_step": Fs * BYTES_IN_PER_FRAME,
+                      "d2h_bytes_per_step": Fs * (3 * 95 * 8 + 12), "lags_match": bool((hs["lags"].numpy() == out["lags"][:Fs].cpu().numpy()).all())}
+        del hs
     del pinned
 
     line = None
@@ -326,6 +341,7 @@ def run_ours(args):
             modes["full_corr_struct"] = time_device(loc, torch, stream, adc[:Fc], None, ("lags", "corr"), k, struct_corr=True)
             modes["full_corr_struct_frames"] = Fc
             extra["modes"] = modes
+            extra["e2e_full_corr_struct"] = e2e_struct
             worst = {}
             for name, flags in (("white_noise", SYNTH_WHITE), ("lowest_snr", SYNTH_MAX_NOISE)):
                 wloc = at.Localizer(device=local_rank, kernel=args.kernel)    # its own context: its own launch history
