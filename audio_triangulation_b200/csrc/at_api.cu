@@ -84,7 +84,8 @@ struct at_context {
     // staging for the host API and the drop-in symbols
     HostSlot slot[2];
     void *d_scratch = nullptr; size_t scratch_bytes = 0;
-    float2 *d_spec = nullptr; size_t spec_frames = 0;   // GCC-PHAT spectra scratch
+    void *d_spec = nullptr; size_t spec_frames = 0;     // GCC-PHAT whitened spectra scratch (half2)
+    float2 *d_gcc_tw = nullptr;                         // GCC-PHAT twiddle table, 2N entries
     // at_average_device: time stamps read back / per-entry decay factors computed on the host
     uint64_t *h_avg_time = nullptr; float *h_avg_decay = nullptr; float *d_avg_decay = nullptr; size_t avg_cap = 0;
     bool umma_window_ok = false;                        // at_fused_umma_window_ok(window)
@@ -146,7 +147,7 @@ extern "C" void at_destroy(at_context *c)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
-                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_peak_tab, c->d_pair_lmax};
+                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_gcc_tw, c->d_peak_tab, c->d_pair_lmax};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &h : c->cert_hist) { if (h.ev) cudaEventDestroy(h.ev); if (h.h_count) cudaFreeHost(h.h_count); }
     if (c->h_avg_time) cudaFreeHost(c->h_avg_time);
@@ -748,8 +749,15 @@ extern "C" int at_gccphat_device(at_context *c, const uint8_t *d_adc, const int3
     if (c->cfg.n_bits != 10 && c->cfg.n_bits != 12) return fail(AT_EINVAL, "GCC-PHAT variant: 1024- or 4096-sample frames only");
     CU(cudaSetDevice(c->cfg.device));
     const size_t M = c->cfg.n_mics, N = c->n_samples, P = c->n_pairs;
-    const size_t per_frame = M * (N + 1) * sizeof(float2);
-    size_t chunk = ((size_t)128 << 20) / per_frame;
+    const size_t per_frame = M * (N + 2) * 4;       // [mics][N + 2] half2
+    if (!c->d_gcc_tw) {
+        std::vector<float2> tw(2 * N);
+        at_gccphat_twiddles(c->cfg.n_bits, tw.data());
+        CU(cudaMalloc(&c->d_gcc_tw, 2 * N * sizeof(float2)));
+        CU(cudaMemcpy(c->d_gcc_tw, tw.data(), 2 * N * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    size_t chunk = ((size_t)64 << 20) / per_frame;      // the whitened spectra of a chunk stay in L2 between the two kernels
+    if (chunk > 65535) chunk = 65535;
     if (chunk < 1) chunk = 1;
     if (chunk > n_frames) chunk = n_frames;
     if (c->spec_frames < chunk) {
@@ -760,7 +768,7 @@ extern "C" int at_gccphat_device(at_context *c, const uint8_t *d_adc, const int3
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const size_t n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
         const cudaError_t e = at_launch_gccphat((int)M, c->cfg.n_bits, c->cfg.max_shift, d_adc + f0 * M * N,
-                                                d_heads ? d_heads + f0 : nullptr, c->d_window, n, c->d_spec, d_lags + f0 * P,
+                                                d_heads ? d_heads + f0 : nullptr, c->d_window, n, c->d_gcc_tw, c->d_spec, d_lags + f0 * P,
                                                 d_peak ? d_peak + f0 * P : nullptr, (cudaStream_t)stream);
         if (e != cudaSuccess) return fail(AT_ECUDA, "GCC-PHAT kernels: %s", cudaGetErrorString(e));
     }

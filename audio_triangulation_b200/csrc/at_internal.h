@@ -100,9 +100,10 @@ cudaError_t at_launch_stream_push(int n_mics, int n_bits, size_t n_arrays, size_
                                   uint8_t *d_hist, long long *d_count, int32_t *d_fired, uint8_t *d_frames, int32_t *d_heads,
                                   cudaStream_t st);
 // at_gccphat.cu -- hand-written FFT / GCC-PHAT variant (crossover study, not a reference algorithm)
+void at_gccphat_twiddles(int n_bits, float2 *h_tw);      // exp(-2 pi i n / 2N), n < 2N
 cudaError_t at_launch_gccphat(int n_mics, int n_bits, int L, const uint8_t *d_adc, const int32_t *d_heads,
-                              const int16_t *d_window, size_t n_frames, float2 *d_spec, int32_t *d_lags, float *d_peak,
-                              cudaStream_t st);
+                              const int16_t *d_window, size_t n_frames, const float2 *d_tw, void *d_spec, int32_t *d_lags,
+                              float *d_peak, cudaStream_t st);
 cudaError_t at_run_microbench(int which, int sm_count, double *gops, double *mhz, cudaStream_t st);
 
 void at_count_launch(unsigned n = 1);

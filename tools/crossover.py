@@ -1,7 +1,8 @@
 """Direct-vs-FFT crossover (BASELINE config 4): 8 mics x 4096 samples, 28 pairs.
-Measured: direct integer correlation on tensor cores (imma, +-46 lags), on the integer pipe (imad), and the
-hand-written FFT/GCC-PHAT variant (cost independent of the lag range).  Model: the direct tensor form costs one
-16x8 IMMA tile per 128 lags, so its time scales with ceil((2L+1+padding)/128); the crossover lag range follows."""
+Measured: direct integer correlation on tensor cores (auto = tcgen05 where it exists, imma = mma.sync; +-46 lags), on
+the integer pipe (imad), and the hand-written FFT/GCC-PHAT variant (cost independent of the lag range).  Model: the
+direct tensor form computes 128-lag tiles (93 used), so its time scales with ceil((2L+1+padding)/128); the crossover
+lag range follows."""
 import json, math, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import audio_triangulation_b200 as at
@@ -15,10 +16,10 @@ def timeit(fn, reps=3):
     return a.elapsed_time(b) / reps
 
 out = {}
-for M, nb, F in ((8, 12, 4096), (3, 10, 1 << 16)):
+for M, nb, F in ((8, 12, 8192), (3, 10, 1 << 17)):
     N = 1 << nb
     row = {}
-    for kernel in ("imma", "imad"):
+    for kernel in ("auto", "imma", "imad"):
         loc = at.Localizer(kernel=kernel, n_mics=M, n_bits=nb)
         adc, _, _ = loc.synth_device(F)
         o = {}
@@ -29,7 +30,7 @@ for M, nb, F in ((8, 12, 4096), (3, 10, 1 << 16)):
     adc, _, _ = loc.synth_device(F)
     ms = timeit(lambda: loc.gccphat_device(adc))
     row["gccphat_frames_per_s"] = F / ms * 1e3
-    ratio = row["imma_frames_per_s"] / row["gccphat_frames_per_s"]
+    ratio = max(row["auto_frames_per_s"], row["imma_frames_per_s"]) / row["gccphat_frames_per_s"]
     # direct tensor cost ~ tiles(L) = ceil((2L + 1 + 3) / 128) (PAD alignment), FFT cost constant
     tiles = math.floor(ratio)
     row["direct_over_fft_at_L46"] = ratio
