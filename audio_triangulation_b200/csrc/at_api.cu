@@ -84,8 +84,9 @@ struct at_context {
     // staging for the host API and the drop-in symbols
     HostSlot slot[2];
     void *d_scratch = nullptr; size_t scratch_bytes = 0;
-    void *d_spec = nullptr; size_t spec_frames = 0;     // GCC-PHAT whitened spectra scratch (half2)
+    void *d_spec = nullptr; size_t spec_bytes = 0;      // GCC-PHAT whitened spectra scratch (half2)
     float2 *d_gcc_tw = nullptr;                         // GCC-PHAT twiddle table, 2N entries
+    void *d_gcc_a = nullptr;                            // GCC-PHAT cos / -sin tiles of the tensor-core inverse (fp16)
     // at_average_device: time stamps read back / per-entry decay factors computed on the host
     uint64_t *h_avg_time = nullptr; float *h_avg_decay = nullptr; float *d_avg_decay = nullptr; size_t avg_cap = 0;
     bool umma_window_ok = false;                        // at_fused_umma_window_ok(window)
@@ -147,7 +148,7 @@ extern "C" void at_destroy(at_context *c)
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
-                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_gcc_tw, c->d_peak_tab, c->d_pair_lmax};
+                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_gcc_tw, c->d_gcc_a, c->d_peak_tab, c->d_pair_lmax};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &h : c->cert_hist) { if (h.ev) cudaEventDestroy(h.ev); if (h.h_count) cudaFreeHost(h.h_count); }
     if (c->h_avg_time) cudaFreeHost(c->h_avg_time);
@@ -749,27 +750,46 @@ extern "C" int at_gccphat_device(at_context *c, const uint8_t *d_adc, const int3
     if (c->cfg.n_bits != 10 && c->cfg.n_bits != 12) return fail(AT_EINVAL, "GCC-PHAT variant: 1024- or 4096-sample frames only");
     CU(cudaSetDevice(c->cfg.device));
     const size_t M = c->cfg.n_mics, N = c->n_samples, P = c->n_pairs;
-    const size_t per_frame = M * (N + 2) * 4;       // [mics][N + 2] half2
+    // inverse side: one tcgen05 contraction over the admissible lags (default) or inverse FFTs (AT_GCC_INVERSE=fft)
+    const char *inv = getenv("AT_GCC_INVERSE");
+    const bool dft = !(inv && !strcmp(inv, "fft")) && c->cfg.max_shift <= 63;
+    const int fgl = dft ? 8 - at_gccphat_dft_ps_log2((int)M) : -1;          // log2 of the frames per column group
+    const size_t FG = dft ? (size_t)1 << fgl : 1;
+    const size_t per_frame = dft ? M * (N / 32) * 144 : M * (N + 2) * 4;    // half2 per (mic, bin); tiled rows of 36 for the contraction
     if (!c->d_gcc_tw) {
         std::vector<float2> tw(2 * N);
         at_gccphat_twiddles(c->cfg.n_bits, tw.data());
         CU(cudaMalloc(&c->d_gcc_tw, 2 * N * sizeof(float2)));
         CU(cudaMemcpy(c->d_gcc_tw, tw.data(), 2 * N * sizeof(float2), cudaMemcpyHostToDevice));
     }
-    size_t chunk = ((size_t)64 << 20) / per_frame;      // the whitened spectra of a chunk stay in L2 between the two kernels
-    if (chunk > 65535) chunk = 65535;
-    if (chunk < 1) chunk = 1;
-    if (chunk > n_frames) chunk = n_frames;
-    if (c->spec_frames < chunk) {
-        if (c->d_spec) { CU(cudaDeviceSynchronize()); cudaFree(c->d_spec); c->d_spec = nullptr; }   // any stream may still be reading it
-        CU(cudaMalloc(&c->d_spec, chunk * per_frame));
-        c->spec_frames = chunk;
+    if (dft && !c->d_gcc_a) {
+        std::vector<uint16_t> a((N / 32) * 8192);
+        at_gccphat_dft_tiles(c->cfg.n_bits, c->cfg.max_shift, a.data());
+        CU(cudaMalloc(&c->d_gcc_a, a.size() * 2));
+        CU(cudaMemcpy(c->d_gcc_a, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
     }
+    // FFT inverse: every spectrum is read by seven pair CTAs, so a chunk's spectra should stay in L2 (64 MB).  Contraction:
+    // read once, but a launch should fill the SMs with column groups a few times over (up to 512 MB).
+    size_t chunk = dft ? ((size_t)512 << 20) / per_frame / ((size_t)c->sm_count * FG) * ((size_t)c->sm_count * FG) : ((size_t)64 << 20) / per_frame;
+    if (dft && chunk < (size_t)c->sm_count * FG) chunk = (size_t)c->sm_count * FG;
+    if (chunk > 65535) chunk = 65535 / FG * FG;
+    if (chunk < FG) chunk = FG;
+    if (chunk > (n_frames + FG - 1) / FG * FG) chunk = (n_frames + FG - 1) / FG * FG;
+    const size_t need = chunk * ((per_frame > M * (N + 2) * 4 ? per_frame : M * (N + 2) * 4) + M * 4);      // either layout, plus the Nyquist bins
+    if (c->spec_bytes < need) {
+        if (c->d_spec) { CU(cudaDeviceSynchronize()); cudaFree(c->d_spec); c->d_spec = nullptr; }   // any stream may still be reading it
+        CU(cudaMalloc(&c->d_spec, need));
+        c->spec_bytes = need;
+    }
+    void *d_nyq = (char *)c->d_spec + chunk * (per_frame > M * (N + 2) * 4 ? per_frame : M * (N + 2) * 4);
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const size_t n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
-        const cudaError_t e = at_launch_gccphat((int)M, c->cfg.n_bits, c->cfg.max_shift, d_adc + f0 * M * N,
-                                                d_heads ? d_heads + f0 : nullptr, c->d_window, n, c->d_gcc_tw, c->d_spec, d_lags + f0 * P,
-                                                d_peak ? d_peak + f0 * P : nullptr, (cudaStream_t)stream);
+        cudaError_t e = at_launch_gccphat((int)M, c->cfg.n_bits, c->cfg.max_shift, d_adc + f0 * M * N,
+                                          d_heads ? d_heads + f0 : nullptr, c->d_window, n, c->d_gcc_tw, c->d_spec, fgl, d_nyq,
+                                          d_lags + f0 * P, d_peak ? d_peak + f0 * P : nullptr, (cudaStream_t)stream);
+        if (e == cudaSuccess && dft)
+            e = at_launch_gccphat_dft((int)M, c->cfg.n_bits, c->cfg.max_shift, n, c->d_gcc_a, c->d_spec, d_nyq, d_lags + f0 * P,
+                                      d_peak ? d_peak + f0 * P : nullptr, (cudaStream_t)stream);
         if (e != cudaSuccess) return fail(AT_ECUDA, "GCC-PHAT kernels: %s", cudaGetErrorString(e));
     }
     return AT_OK;

@@ -178,7 +178,8 @@ __device__ __forceinline__ int fft_out_index(int t, int q)
 
 template <int NBITS>
 __global__ void __launch_bounds__((1 << NBITS) / 8, 8192 >> NBITS) gcc_forward_kernel(const uint8_t *adc, const int32_t *heads, const int16_t *window,
-                                                                       int n_mics, const float2 *__restrict__ tw, __half2 *spec /*[F][M][N+2]*/)
+                                                                       int n_mics, const float2 *__restrict__ tw, __half2 *spec /*[F][M][N+2], or tiled*/,
+                                                                                      int fg_log2, __half2 *nyq)
 {
     constexpr int N = 1 << NBITS, N2 = 2 * N, T = N / 8;
     using G = FftGeo<N>;
@@ -223,7 +224,12 @@ __global__ void __launch_bounds__((1 << NBITS) / 8, 8192 >> NBITS) gcc_forward_k
     __syncthreads();
     // Z = A + i B with A, B the spectra of the two real channels: A[m] = (Z[m] + conj Z[-m]) / 2, B[m] = (Z[m] - conj Z[-m]) / 2i;
     // whitened (PHAT): U = X / |X|
+    // fg_log2 < 0: [frame][mic][N + 2] (pair kernel).  Else, for the tensor-core inverse (at_gccphat_dft.cu): one contiguous tile
+    // per (group of 2^fg_log2 frames, chunk of 32 bins): [group][chunk][frame in group][mic][36]; bin N goes to nyq[frame][mic]
     __half2 *ua = spec + (f * n_mics + ca) * (size_t)(N + 2), *ub = cb >= 0 ? spec + (f * n_mics + cb) * (size_t)(N + 2) : nullptr;
+    // (rows of 36 half2, 32 used: 144-byte rows keep the converter threads' 16-byte reads of different mics off each other's banks)
+    const size_t tile = ((size_t)n_mics << (fg_log2 < 0 ? 0 : fg_log2)) * 36;                       // half2 per chunk tile
+    const size_t tbase = fg_log2 < 0 ? 0 : (f >> fg_log2) * (size_t)(N / 32) * tile + (f & ((1u << fg_log2) - 1)) * (size_t)n_mics * 36;
     for (int m = t; m <= N; m += T) {
         const int odd = m & 1, k = m >> 1, kc = odd ? N - 1 - k : (N - k) & (N - 1);     // Z[2N - m]: same parity
         const int a = odd * G::WORDS + fft_pad(k), ac = odd * G::WORDS + fft_pad(kc);
@@ -231,8 +237,18 @@ __global__ void __launch_bounds__((1 << NBITS) / 8, 8192 >> NBITS) gcc_forward_k
         float2 A = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y)), B = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
         const float ma = A.x * A.x + A.y * A.y, mb = B.x * B.x + B.y * B.y;
         const float ia = ma > 1e-30f ? rsqrtf(ma) : 0.f, ib = mb > 1e-30f ? rsqrtf(mb) : 0.f;
-        ua[m] = __floats2half2_rn(A.x * ia, A.y * ia);       // unit magnitude: half precision costs 2^-11 of phase
-        if (ub) ub[m] = __floats2half2_rn(B.x * ib, B.y * ib);
+        const __half2 ha = __floats2half2_rn(A.x * ia, A.y * ia), hb = __floats2half2_rn(B.x * ib, B.y * ib);   // unit magnitude: half precision costs 2^-11 of phase
+        if (fg_log2 < 0) {
+            ua[m] = ha;
+            if (ub) ub[m] = hb;
+        } else if (m < N) {
+            __half2 *d = spec + tbase + (size_t)(m >> 5) * tile + (m & 31);
+            d[(size_t)ca * 36] = ha;
+            if (cb >= 0) d[(size_t)cb * 36] = hb;
+        } else {
+            nyq[f * n_mics + ca] = ha;
+            if (cb >= 0) nyq[f * n_mics + cb] = hb;
+        }
     }
     (void)N2;
 }
@@ -338,9 +354,11 @@ void at_gccphat_twiddles(int n_bits, float2 *h_tw)
     }
 }
 
+// fg_log2 < 0: forward + pair kernels (inverse FFTs).  fg_log2 >= 0: forward kernel only, spectra tiled for the tensor-core
+// inverse (at_launch_gccphat_dft), d_nyq = bin N of every (frame, mic).
 cudaError_t at_launch_gccphat(int n_mics, int n_bits, int L, const uint8_t *d_adc, const int32_t *d_heads,
-                              const int16_t *d_window, size_t n_frames, const float2 *d_tw, void *d_spec, int32_t *d_lags,
-                              float *d_peak, cudaStream_t st)
+                              const int16_t *d_window, size_t n_frames, const float2 *d_tw, void *d_spec, int fg_log2, void *d_nyq,
+                              int32_t *d_lags, float *d_peak, cudaStream_t st)
 {
     if (!n_frames) return cudaSuccess;
     const int P = n_mics * (n_mics - 1) / 2;
@@ -353,13 +371,13 @@ cudaError_t at_launch_gccphat(int n_mics, int n_bits, int L, const uint8_t *d_ad
         if (L >= (1 << NB) / 8) return cudaErrorInvalidValue;      /* lag window vs the pruned last pass */                       \
         if ((e = cudaFuncSetAttribute(gcc_forward_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e; \
         if ((e = cudaFuncSetAttribute(gcc_pair_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;    \
-        gcc_forward_kernel<NB><<<g1, (1 << NB) / 8, smem, st>>>(d_adc, d_heads, d_window, n_mics, d_tw, (__half2 *)d_spec); \
-        gcc_pair_kernel<NB><<<g2, (1 << NB) / 8, smem, st>>>((const __half2 *)d_spec, n_mics, L, d_tw, d_lags, d_peak);          \
+        gcc_forward_kernel<NB><<<g1, (1 << NB) / 8, smem, st>>>(d_adc, d_heads, d_window, n_mics, d_tw, (__half2 *)d_spec, fg_log2, (__half2 *)d_nyq); \
+        if (fg_log2 < 0) gcc_pair_kernel<NB><<<g2, (1 << NB) / 8, smem, st>>>((const __half2 *)d_spec, n_mics, L, d_tw, d_lags, d_peak); \
     }
     if (n_bits == 10) AT_GCC(10)
     else if (n_bits == 12) AT_GCC(12)
     else return cudaErrorInvalidValue;
 #undef AT_GCC
-    at_count_launch(2);
+    at_count_launch(fg_log2 < 0 ? 2 : 1);
     return cudaGetLastError();
 }

@@ -102,8 +102,13 @@ cudaError_t at_launch_stream_push(int n_mics, int n_bits, size_t n_arrays, size_
 // at_gccphat.cu -- hand-written FFT / GCC-PHAT variant (crossover study, not a reference algorithm)
 void at_gccphat_twiddles(int n_bits, float2 *h_tw);      // exp(-2 pi i n / 2N), n < 2N
 cudaError_t at_launch_gccphat(int n_mics, int n_bits, int L, const uint8_t *d_adc, const int32_t *d_heads,
-                              const int16_t *d_window, size_t n_frames, const float2 *d_tw, void *d_spec, int32_t *d_lags,
-                              float *d_peak, cudaStream_t st);
+                              const int16_t *d_window, size_t n_frames, const float2 *d_tw, void *d_spec, int fg_log2, void *d_nyq,
+                              int32_t *d_lags, float *d_peak, cudaStream_t st);
+// at_gccphat_dft.cu -- the inverse side as one tcgen05 contraction with a constant cos / -sin operand
+void at_gccphat_dft_tiles(int n_bits, int L, uint16_t *h_out);     // (N / 32) * 8192 fp16 entries
+int at_gccphat_dft_ps_log2(int n_mics);                            // pair slots per frame = 2^this; frames per group = 256 >> this
+cudaError_t at_launch_gccphat_dft(int n_mics, int n_bits, int L, size_t n_frames, const void *d_a_tiles, const void *d_spec_tiled,
+                                  const void *d_nyq, int32_t *d_lags, float *d_peak, cudaStream_t st);
 cudaError_t at_run_microbench(int which, int sm_count, double *gops, double *mhz, cudaStream_t st);
 
 void at_count_launch(unsigned n = 1);

@@ -22,10 +22,12 @@ def numpy_gccphat(windowed, L):
     return np.stack(out, 1).astype(np.int32)
 
 
-@pytest.mark.parametrize("shape", [(3, 10, 128), (8, 12, 24), (8, 10, 64)])
-def test_gccphat_lags_agree_with_float64(shape):
+@pytest.mark.parametrize("inverse", ["dft", "fft"])       # tcgen05 contraction over the wanted lags / inverse FFTs
+@pytest.mark.parametrize("shape", [(3, 10, 128), (8, 12, 24), (8, 10, 64), (4, 10, 37), (8, 12, 300)])
+def test_gccphat_lags_agree_with_float64(shape, inverse, monkeypatch):
     import torch
     import audio_triangulation_b200 as at
+    monkeypatch.setenv("AT_GCC_INVERSE", inverse)
     M, nb, F = shape
     loc = at.Localizer(n_mics=M, n_bits=nb)
     adc, heads, _ = loc.synth_device(F, flags=1 | 2, seed=99)             # integer delays, random ring heads
@@ -40,3 +42,18 @@ def test_gccphat_lags_agree_with_float64(shape):
     # PHAT and the direct integer correlation find the same TDOA on clean integer-delay bursts most of the time
     direct = res["lags"].cpu().numpy()
     assert (np.abs(got - direct) <= 1).mean() >= 0.85
+
+
+def test_gccphat_inverse_forms_agree(monkeypatch):
+    """The two inverse forms see the same whitened spectra: their arg-max lags differ only at float near-ties."""
+    import torch
+    import audio_triangulation_b200 as at
+    loc = at.Localizer(n_mics=8, n_bits=12)
+    adc, heads, _ = loc.synth_device(515, flags=2, seed=5)                # ragged: not a multiple of the 8-frame column group
+    out = {}
+    for inverse in ("dft", "fft"):
+        monkeypatch.setenv("AT_GCC_INVERSE", inverse)
+        out[inverse] = loc.gccphat_device(adc, heads).cpu().numpy()
+    torch.cuda.synchronize()
+    assert (out["dft"] == out["fft"]).mean() >= 0.995
+    loc.close()
