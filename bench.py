@@ -371,6 +371,22 @@ def run_ours(args):
                                     "lags_position_frames_per_s": time_device(loc8, torch, stream, adc8, None, ("lags", "cell", "xy"), k),
                                     "int16_tmac_per_s": None}
                 extra["config4"]["int16_tmac_per_s"] = extra["config4"]["lags_frames_per_s"] * 28 * (93 * 4096 - 2162) / 1e12
+                # the hand-written FFT / GCC-PHAT variant on the same batch (another statistic: lags agree, curves do not):
+                # forward radix-8 FFTs + one tcgen05 fp16 contraction over the +-46 lags; its cost does not depend on the lag
+                # range up to +-63, the direct form's does (one 128-row tile covers 93 + 16 lags)
+                g8 = loc8.gccphat_device(adc8)
+                torch.cuda.synchronize(dev)
+                t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0e.record()
+                for _ in range(k):
+                    loc8.gccphat_device(adc8)
+                t1e.record()
+                torch.cuda.synchronize(dev)
+                gps = F8 * k / (t0e.elapsed_time(t1e) * 1e-3)
+                d8 = loc8.localize_device(adc8, None, want=("lags",))["lags"]
+                extra["config4"]["gccphat_frames_per_s"] = gps
+                extra["config4"]["gccphat_lag_agreement_with_direct"] = float((g8 == d8).float().mean().item())
+                extra["config4"]["direct_over_gccphat"] = extra["config4"]["lags_frames_per_s"] / gps
                 del adc8
                 loc8.close()
             except Exception as e:   # pragma: no cover
