@@ -44,6 +44,18 @@ for nb, kernel in ((12, "auto"), (10, "umma"), (10, "imma")):
     assert (r["cell"].cpu().numpy() == o["cell"]).all(), (nb, kernel)
     print("8 mics", nb, kernel, "ok")
     loc.close()
+# FFT / GCC-PHAT variant, both inverse forms, ragged sizes (partial column groups)
+for M, nb, F in ((8, 12, 13), (3, 10, 131), (4, 10, 40)):
+    loc = at.Localizer(n_mics=M, n_bits=nb)
+    adc, heads, _ = loc.synth_device(F, flags=2)
+    res = {}
+    for inv in ("dft", "fft"):
+        os.environ["AT_GCC_INVERSE"] = inv
+        res[inv] = loc.gccphat_device(adc, heads).cpu().numpy()
+    os.environ.pop("AT_GCC_INVERSE")
+    assert (res["dft"] == res["fft"]).mean() > 0.98, (M, nb)
+    print("gcc-phat", M, nb, "ok")
+    loc.close()
 loc = at.Localizer()
 adc, heads, _ = loc.synth_device(67, flags=2 | 4)
 st = at.Stream(loc, 5)
