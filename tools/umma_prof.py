@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import audio_triangulation_b200 as at
 loc = at.Localizer(kernel="umma")
 F = 1 << 19
-adc, _, _ = loc.synth_device(F)
+flags = int(os.environ.get("AT_SYNTH_FLAGS", "0"))            # 16: white noise (every frame takes the exact pass and the full scan)
+adc, _, _ = loc.synth_device(F, flags=flags)
 want = tuple(sys.argv[1:]) or ("lags", "cell", "xy")
 os.environ.pop("AT_PROF_PRINT", None)
 out = {}
