@@ -59,7 +59,9 @@ extern "C" uint64_t at_get_time_us(void)
 
 // ------------------------------------------------------------------ context
 struct HostSlot {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                       // the slot's kernels
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;   // input landed / kernels done / results copied out
+    bool used = false;
     size_t cap_frames = 0;
     uint8_t *adc = nullptr; int32_t *heads = nullptr;
     int32_t *lags = nullptr; void *corr = nullptr; long long *raw = nullptr; int32_t *cell = nullptr;
@@ -82,7 +84,11 @@ struct at_context {
     std::vector<float> h_mic_xy; std::vector<uint8_t> h_lut; std::vector<int32_t> h_delay_q8;
     std::vector<float> h_points;   // AT_LUT_POINTS: candidate positions [cells][3]
     // staging for the host API and the drop-in symbols
-    HostSlot slot[2];
+    // at_localize_host: chunks rotate over three slots; every host->device copy goes through copy_in and every device->host
+    // copy through copy_out (one stream per direction keeps both copy engines busy: with H2D, kernel and D2H of a chunk on
+    // ONE stream the two directions reach 34 GB/s each on this platform instead of 49, tools/pcie_duplex.py)
+    HostSlot slot[3];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
     void *d_scratch = nullptr; size_t scratch_bytes = 0;
     void *d_spec = nullptr; size_t spec_bytes = 0;      // GCC-PHAT whitened spectra scratch (half2)
     float2 *d_gcc_tw = nullptr;                         // GCC-PHAT twiddle table, 2N entries
@@ -146,7 +152,10 @@ extern "C" void at_destroy(at_context *c)
         void *ptrs[] = {s.adc, s.heads, s.lags, s.corr, s.raw, s.cell, s.highest, s.xy, s.gate, s.classes, s.windowed, s.power};
         for (void *p : ptrs) if (p) cudaFree(p);
         if (s.stream) cudaStreamDestroy(s.stream);
+        for (cudaEvent_t ev : {s.ev_in, s.ev_k, s.ev_out}) if (ev) cudaEventDestroy(ev);
     }
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
                     c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_gcc_tw, c->d_gcc_a, c->d_peak_tab, c->d_pair_lmax};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -188,7 +197,14 @@ static int create_impl(const at_config *cfg, at_context *c)
         return fail(AT_EINVAL, "AT_LUT_POINTS needs 1..4194304 candidate positions");
     c->n_cells = points ? cfg->n_points : (2 * cfg->half_w + 1) * (2 * cfg->half_h + 1);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto &s : c->slot) CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (auto &s : c->slot) {
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    }
+    CU(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
 
     // geometry (ref: microphones.c) and lag LUT (ref: vga_heatmap.h:50-92), both on the device
     CU(cudaMalloc(&c->d_mic_xy, sizeof(float) * 2 * AT_MAX_MICS));
@@ -384,6 +400,8 @@ extern "C" int at_synchronize(at_context *c)
     CU(cudaSetDevice(c->cfg.device));
     CU(cudaStreamSynchronize(c->stream));
     for (auto &s : c->slot) CU(cudaStreamSynchronize(s.stream));
+    CU(cudaStreamSynchronize(c->copy_in));
+    CU(cudaStreamSynchronize(c->copy_out));
     return AT_OK;
 }
 
@@ -576,7 +594,7 @@ static int host_async(at_context *c, const uint8_t *h_adc, const int32_t *h_head
             void **ptrs[] = {(void **)&s.adc, (void **)&s.heads, (void **)&s.lags, &s.corr, (void **)&s.raw, (void **)&s.cell,
                              (void **)&s.highest, (void **)&s.xy, (void **)&s.gate, (void **)&s.classes,
                              (void **)&s.windowed, (void **)&s.power};
-            CU(cudaStreamSynchronize(s.stream));
+            CU(cudaDeviceSynchronize());
             for (void **p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
             s.cap_frames = C;
         }
@@ -597,10 +615,16 @@ static int host_async(at_context *c, const uint8_t *h_adc, const int32_t *h_head
     const AtShape sh = {c->cfg.n_mics, c->cfg.n_bits, c->cfg.max_shift};
     size_t k = 0;
     for (size_t f0 = 0; f0 < n_frames; f0 += C, k++) {
-        HostSlot &s = c->slot[k & 1];
+        HostSlot &s = c->slot[k % 3];
         const size_t n = n_frames - f0 < C ? n_frames - f0 : C;
-        CU(cudaMemcpyAsync(s.adc, h_adc + f0 * M * N, n * M * N, cudaMemcpyHostToDevice, s.stream));
-        if (h_heads) CU(cudaMemcpyAsync(s.heads, h_heads + f0, n * 4, cudaMemcpyHostToDevice, s.stream));
+        // in: after the kernels of the chunk that used this slot before have read its input
+        if (s.used) CU(cudaStreamWaitEvent(c->copy_in, s.ev_k, 0));
+        CU(cudaMemcpyAsync(s.adc, h_adc + f0 * M * N, n * M * N, cudaMemcpyHostToDevice, c->copy_in));
+        if (h_heads) CU(cudaMemcpyAsync(s.heads, h_heads + f0, n * 4, cudaMemcpyHostToDevice, c->copy_in));
+        CU(cudaEventRecord(s.ev_in, c->copy_in));
+        // kernels: after the input has landed and the previous results of this slot have left
+        CU(cudaStreamWaitEvent(s.stream, s.ev_in, 0));
+        if (s.used) CU(cudaStreamWaitEvent(s.stream, s.ev_out, 0));
         AtFusedParams p;
         memset(&p, 0, sizeof p);
         p.adc = s.adc; p.heads = h_heads ? s.heads : nullptr; p.n_frames = n;
@@ -612,9 +636,11 @@ static int host_async(at_context *c, const uint8_t *h_adc, const int32_t *h_head
         p.now_us = at_get_time_us();
         const int rc = launch_fused(c, sh, p, c->cfg.kernel, s.stream);
         if (rc != AT_OK) return rc;
+        CU(cudaEventRecord(s.ev_k, s.stream));
+        CU(cudaStreamWaitEvent(c->copy_out, s.ev_k, 0));
 #define D2H(field, dst, bytes_per_frame)                                                                   \
     if (dst) CU(cudaMemcpyAsync((char *)(dst) + f0 * (bytes_per_frame), s.field, n * (bytes_per_frame),    \
-                                cudaMemcpyDeviceToHost, s.stream));
+                                cudaMemcpyDeviceToHost, c->copy_out));
         D2H(lags, o->lags, P * 4)
         D2H(corr, o->corr, corr_bytes)
         D2H(raw, o->raw, P * NL * 8)
@@ -626,8 +652,20 @@ static int host_async(at_context *c, const uint8_t *h_adc, const int32_t *h_head
         D2H(windowed, o->windowed, M * N * 2)
         D2H(power, o->power, M * 8)
 #undef D2H
+        CU(cudaEventRecord(s.ev_out, c->copy_out));
+        s.used = true;
     }
     return AT_OK;
+}
+
+// everything at_localize_host* has in flight on this context
+static bool host_streams_sync(at_context *c)
+{
+    bool ok = true;
+    for (auto &s : c->slot) ok &= cudaStreamSynchronize(s.stream) == cudaSuccess;
+    ok &= cudaStreamSynchronize(c->copy_in) == cudaSuccess;
+    ok &= cudaStreamSynchronize(c->copy_out) == cudaSuccess;
+    return ok;
 }
 
 extern "C" int at_localize_host(at_context *c, const uint8_t *h_adc, const int32_t *h_heads, size_t n_frames,
@@ -637,9 +675,7 @@ extern "C" int at_localize_host(at_context *c, const uint8_t *h_adc, const int32
     if (!n_frames) return AT_OK;
     const int rc = host_async(c, h_adc, h_heads, n_frames, o);
     // also on an error: copies into the caller's host arrays may be in flight from the chunks already launched
-    int rc_sync = AT_OK;
-    for (auto &s : c->slot)
-        if (cudaStreamSynchronize(s.stream) != cudaSuccess) rc_sync = AT_ECUDA;
+    const int rc_sync = host_streams_sync(c) ? AT_OK : AT_ECUDA;
     if (rc != AT_OK) return rc;
     if (rc_sync != AT_OK) return fail(AT_ECUDA, "at_localize_host: %s", cudaGetErrorString(cudaGetLastError()));
     return AT_OK;
@@ -667,8 +703,7 @@ extern "C" int at_localize_host_sharded(at_context **ctxs, int n_ctx, const uint
     // wait for every context touched, also after an error (D2H copies into the caller's arrays may be in flight)
     for (int g = 0; g < n_ctx; g++) {
         if (cudaSetDevice(ctxs[g]->cfg.device) != cudaSuccess) continue;
-        for (auto &s : ctxs[g]->slot)
-            if (cudaStreamSynchronize(s.stream) != cudaSuccess && rc_all == AT_OK) rc_all = fail(AT_ECUDA, "at_localize_host_sharded: stream synchronisation failed");
+        if (!host_streams_sync(ctxs[g]) && rc_all == AT_OK) rc_all = fail(AT_ECUDA, "at_localize_host_sharded: stream synchronisation failed");
     }
     return rc_all;
 }
