@@ -199,8 +199,9 @@ typedef struct at_outputs {
  * frame (NULL = all 0 = chronological).  Asynchronous on `stream`. */
 int at_localize_device(at_context *ctx, const uint8_t *d_adc, const int32_t *d_heads, size_t n_frames,
                        const at_outputs *d_out, void *stream);
-/* Same from host memory: chunks the batch, overlaps H2D / kernel / D2H on two streams, returns
- * when all results are in host memory.  Pinned host buffers are copied directly. */
+/* Same from host memory: chunks the batch over three device slots, host->device copies on one stream, kernels on
+ * the slot's stream, device->host copies on a third (both copy directions stay busy); returns when all results
+ * are in host memory.  Pinned host buffers are copied directly. */
 int at_localize_host(at_context *ctx, const uint8_t *h_adc, const int32_t *h_heads, size_t n_frames,
                      const at_outputs *h_out);
 /* Frame-sharded over several contexts (one per GPU) driven from one host thread: context g gets
