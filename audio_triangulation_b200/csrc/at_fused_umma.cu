@@ -117,6 +117,7 @@ struct UmmaSmem {
     // exact variant
     alignas(16) EpiSmem<3, 10, L> epi[CERT ? 1 : G::SETS];       // raw curves by lag index + scratch of the group epilogue
     alignas(16) long long part64[CERT ? 1 : G::SETS][3][4];      // per-warp arg-max keys
+    int boxok[G::SETS];                                          // exact pass over the redo list: did the bounded search settle the frame?
     alignas(16) int spill[CERT ? 1 : G::SETS][2][6][3][32];      // partial sums that cross a lane quarter: [array][quarter below][lane]
     alignas(16) uint32_t meta[G::META][4];              // per frame: sum of squared low digits of each channel
     float gauss[2 * L + 1];
@@ -557,6 +558,17 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                         settled = peak_tuple_lookup<L>(p, f, m, best3[0], best3[1], best3[2], peak);
                     // everything else -- whole curves, flat or inconsistent curves -- by the whole set: Gaussian re-weighting,
                     // result stores and the likelihood maximum over all LUT tuples with 128 threads
+                    // a frame the certified pass could not settle usually has peaked curves whose three lags miss the LUT by one:
+                    // one warp's exact bounded search around the peak tuple (at_imma_common.cuh) decides most of them; frames of
+                    // an exact-only launch (whole curves, or input that certifies nothing) go straight to the full scan
+                    if (!settled && p.frame_list && !(p.raw || p.corr || p.classes)) {
+                        if (wq == 0) {
+                            const bool ok = epilogue_warp<L, PAD, G::NJ, G::NJ, false>(&epi.curve[0][0], best3[0], best3[1], best3[2], s.gauss, p, f, lane);
+                            if (lane == 0) s.boxok[set] = ok ? 1 : 0;
+                        }
+                        named_bar(bar_b, 128);
+                        settled = s.boxok[set] != 0;
+                    }
                     if (!settled) {
                         if (m == 0 && p.stats && (p.cell || p.highest || p.xy || p.classes)) atomicAdd(&p.stats[2], 1ull);   // route: full scan
                         epilogue<3, 10, L, 128>(epi, s.gauss, p, f, m, bar_a);
