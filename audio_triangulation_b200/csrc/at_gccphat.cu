@@ -93,20 +93,28 @@ __device__ __forceinline__ void fft_twiddle_dft(float2 (&v)[8], int t, int Ns, c
         }
     }
 }
+// pad(a + c) = pad(a) + pad(c) when c is a multiple of 64 (no carry into the pad terms): the element addresses of a pass
+// are one fft_pad per thread plus compile-time offsets
+__host__ __device__ constexpr int fft_pad_c(int c) { return c + (c >> 5) + ((c >> 6) << 3); }
 template <int N, int R>
 __device__ __forceinline__ void fft_store(const float2 (&v)[8], int t, int Ns, float *re, float *im)
 {
     constexpr int T = N / 8;
     if constexpr (R == 8) {
-        const int k = t & (Ns - 1), j0 = (t - k) * 8 + k;
+        const int k = t & (Ns - 1), j0 = (t - k) * 8 + k, a0 = fft_pad(j0);
 #pragma unroll
-        for (int r = 0; r < 8; r++) { const int a = fft_pad(j0 + r * Ns); re[a] = v[r].x; im[a] = v[r].y; }
+        for (int r = 0; r < 8; r++) {
+            // Ns = 1: j0 = 8 t, + r stays inside the 32-word block.  Ns = 8: j0 = 64 (t / 8) + t % 8, + 8 r stays inside the
+            // 64-word block and crosses its 32-word half at r = 4.  Ns >= 64: multiples of 64.
+            const int a = Ns == 1 ? a0 + r : (Ns == 8 ? a0 + 8 * r + (r >= 4 ? 1 : 0) : a0 + r * fft_pad_c(Ns));
+            re[a] = v[r].x; im[a] = v[r].y;
+        }
     } else {
 #pragma unroll
         for (int b = 0; b < 2; b++) {
-            const int j = t + b * T, k = j & (Ns - 1), j0 = (j - k) * 4 + k;
+            const int j = t + b * T, k = j & (Ns - 1), j0 = (j - k) * 4 + k, a0 = fft_pad(j0);      // radix-4 passes have Ns >= 64
 #pragma unroll
-            for (int r = 0; r < 4; r++) { const int a = fft_pad(j0 + r * Ns); re[a] = v[4 * b + r].x; im[a] = v[4 * b + r].y; }
+            for (int r = 0; r < 4; r++) { const int a = a0 + r * fft_pad_c(Ns); re[a] = v[4 * b + r].x; im[a] = v[4 * b + r].y; }
         }
     }
 }
@@ -114,14 +122,16 @@ template <int N, int R>
 __device__ __forceinline__ void fft_load(float2 (&v)[8], int t, const float *re, const float *im)
 {
     constexpr int T = N / 8;
+    static_assert(T % 64 == 0, "offsets of a thread's elements are multiples of 64");
+    const int a0 = fft_pad(t);
     if constexpr (R == 8) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) { const int a = fft_pad(t + r * T); v[r] = make_float2(re[a], im[a]); }
+        for (int r = 0; r < 8; r++) { const int a = a0 + fft_pad_c(r * T); v[r] = make_float2(re[a], im[a]); }
     } else {
 #pragma unroll
         for (int b = 0; b < 2; b++)
 #pragma unroll
-            for (int r = 0; r < 4; r++) { const int a = fft_pad(t + b * T + r * 2 * T); v[4 * b + r] = make_float2(re[a], im[a]); }
+            for (int r = 0; r < 4; r++) { const int a = a0 + fft_pad_c(b * T + r * 2 * T); v[4 * b + r] = make_float2(re[a], im[a]); }
     }
 }
 
