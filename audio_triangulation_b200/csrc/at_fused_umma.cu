@@ -126,19 +126,6 @@ struct UmmaSmem {
     uint32_t tmem_base;
 };
 
-// 16 bytes starting sh bytes (1..15) into the 32-byte pair (a, b); sh is warp-uniform (one ring head per frame), so the
-// word offset is a branch, not a chain of selects
-__device__ __forceinline__ uint4 realign16(const uint4 a, const uint4 b, int sh)
-{
-    const int ws = sh >> 2, bs = (sh & 3) * 8;
-    uint32_t t0, t1, t2, t3, t4;
-    if (ws == 0) { t0 = a.x; t1 = a.y; t2 = a.z; t3 = a.w; t4 = b.x; }
-    else if (ws == 1) { t0 = a.y; t1 = a.z; t2 = a.w; t3 = b.x; t4 = b.y; }
-    else if (ws == 2) { t0 = a.z; t1 = a.w; t2 = b.x; t3 = b.y; t4 = b.z; }
-    else { t0 = a.w; t1 = b.x; t2 = b.y; t3 = b.z; t4 = b.w; }
-    return make_uint4(__funnelshift_r(t0, t1, bs), __funnelshift_r(t1, t2, bs), __funnelshift_r(t2, t3, bs), __funnelshift_r(t3, t4, bs));
-}
-
 // 16 ring-ordered ADC bytes of chronological samples [i0, i0 + 16) of one channel (staged in shared memory), any head
 __device__ __forceinline__ uint4 load_chrono16(const uint8_t *chan, int i0, int head)
 {

@@ -160,11 +160,16 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
             uint8_t *const ph = &s.planes[b][(2 * ch) * PLANE], *const pl = ph + PLANE;
             const uint8_t *src = p.adc + (f * NM + ch) * (unsigned long long)N;
             const int head = p.heads ? (p.heads[f] & (N - 1)) : 0;
+            const int uhead = __shfl_sync(0xffffffffu, head, 0);      // tells the compiler what it cannot see: warp-uniform
             uint4 raw[Q];
             unsigned sum = 0;
 #pragma unroll
             for (int q = 0; q < Q; q++) {
-                const uint4 x = ldg_stream(src + q * 512 + lane * 16);
+                // the lane's chronological samples [512 q + 16 l, +16), un-rotated from the ring: one aligned 16-byte load, or two
+                // and a byte shift when the head is not 16-aligned (warp-uniform branch)
+                const int r = (q * 512 + lane * 16 + uhead) & (N - 1), r0 = r & ~15, sh = r & 15;
+                uint4 x = ldg_stream(src + r0);
+                if (sh) x = realign16(x, ldg_stream(src + ((r0 + 16) & (N - 1))), sh);
                 raw[q] = x;
                 sum = __dp4a(x.x, 0x01010101u, sum); sum = __dp4a(x.y, 0x01010101u, sum);
                 sum = __dp4a(x.z, 0x01010101u, sum); sum = __dp4a(x.w, 0x01010101u, sum);
@@ -178,32 +183,18 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
             if (v >= 1) mbar_wait(&s.sfree[b], (v - 1) & 1);            // the tensor core is done with frame i - 2
 #pragma unroll
             for (int q = 0; q < Q; q++) {
-                const int j0 = q * 512 + lane * 16;
+                const int i0 = q * 512 + lane * 16;
                 const uint32_t rw[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
-                if ((head & 15) == 0) {
-                    const int i0 = (j0 - head) & (N - 1);
-                    uint32_t hi[4], lo[4];
-                    umma_prep16(rw, mean, s.win2, i0, hi, lo);
-                    *reinterpret_cast<uint4 *>(ph + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4 *>(pl + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    if (G::COPIES == 2) {   // second copy, advanced by 8 bytes: sample i sits at PAD - 8 + i
-                        uint8_t *const ph2 = ph + 2 * NM * PLANE, *const pl2 = ph2 + PLANE;
-                        *reinterpret_cast<uint2 *>(ph2 + PAD - 8 + i0) = make_uint2(hi[0], hi[1]);
-                        *reinterpret_cast<uint2 *>(ph2 + PAD + i0) = make_uint2(hi[2], hi[3]);
-                        *reinterpret_cast<uint2 *>(pl2 + PAD - 8 + i0) = make_uint2(lo[0], lo[1]);
-                        *reinterpret_cast<uint2 *>(pl2 + PAD + i0) = make_uint2(lo[2], lo[3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; e++) {
-                        const int ii = (j0 + e - head) & (N - 1);
-                        const int q24 = imma_prep1(rw[e >> 2] >> (8 * (e & 3)), mean, s.win2, ii) + 0x8000;
-                        ph[PAD + ii] = (uint8_t)(q24 >> 16); pl[PAD + ii] = (uint8_t)((q24 >> 8) ^ 0x80);
-                        if (G::COPIES == 2) {
-                            ph[2 * NM * PLANE + PAD - 8 + ii] = (uint8_t)(q24 >> 16);
-                            pl[2 * NM * PLANE + PAD - 8 + ii] = (uint8_t)((q24 >> 8) ^ 0x80);
-                        }
-                    }
+                uint32_t hi[4], lo[4];
+                umma_prep16(rw, mean, s.win2, i0, hi, lo);
+                *reinterpret_cast<uint4 *>(ph + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(pl + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                if (G::COPIES == 2) {   // second copy, advanced by 8 bytes: sample i sits at PAD - 8 + i
+                    uint8_t *const ph2 = ph + 2 * NM * PLANE, *const pl2 = ph2 + PLANE;
+                    *reinterpret_cast<uint2 *>(ph2 + PAD - 8 + i0) = make_uint2(hi[0], hi[1]);
+                    *reinterpret_cast<uint2 *>(ph2 + PAD + i0) = make_uint2(hi[2], hi[3]);
+                    *reinterpret_cast<uint2 *>(pl2 + PAD - 8 + i0) = make_uint2(lo[0], lo[1]);
+                    *reinterpret_cast<uint2 *>(pl2 + PAD + i0) = make_uint2(lo[2], lo[3]);
                 }
             }
             if (p.power) {   // rolling_buffer.c:68-70
