@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
 {
     using G = UmmaMGeo<NBITS, L>;
     using S = UmmaMSmem<NBITS, L>;
-    constexpr int N = G::N, PAD = G::PAD, PLANE = G::PLANE, NM = G::NM, P = G::P, NJ = G::NJ;
+    constexpr int N = G::N, PAD = G::PAD, PLANE = G::PLANE, NM = G::NM, NJ = G::NJ;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     S &s = *reinterpret_cast<S *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -220,7 +220,14 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
         for (unsigned long long i = 0;; i++) {
             const unsigned long long f = blockIdx.x + gstride * i;
             if (f >= nf) break;
-            for (int k = et; k < P * NJ; k += G::EPI_THREADS) curvef[k] = 0;
+            // Passes 2i and 2i+1 hold the two digits of the same (pair, lag) items in the same order: a thread keeps the y.h sum in a
+            // register and stores the finished entry after the y.l pass -- no read-modify-write, no zeroing.  Only the last pass
+            // {4h, 4l} adds both digits of its four pairs (x, 4) in one go (atomics on entries zeroed here).
+            if (et < 4 * NJ) {
+                const int x = et / NJ;
+                curvef[(x * NM - x * (x + 1) / 2 + (4 - x - 1)) * NJ + (et - x * NJ)] = 0;
+            }
+            long long keep[2] = {0, 0};
             named_bar(1, G::EPI_THREADS);
 #pragma unroll 1
             for (int g = 0; g < G::PASSES; g++) {
@@ -267,7 +274,8 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
                     AT_CHECK((int)(tt >> 8) < NM * (NM - 1) / 2 && j >= 0 && j < NJ && j + G::PH - 1 + (G::PH - 1) * G::ZP < G::PH * G::ZP + G::ZP);
                     long long *const dst = &curvef[(tt >> 8) * NJ + j];
                     if (g == G::PASSES - 1) atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)(sum << (tt & 31)));
-                    else *dst += sum << (tt & 31);
+                    else if ((g & 1) == 0) keep[q] = sum << 8;          // y.h
+                    else *dst = keep[q] + sum;                          // y.l completes the entry
                 }
                 named_bar(1, G::EPI_THREADS);
             }
