@@ -61,7 +61,7 @@ struct UmmaMSmem {
     alignas(128) uint8_t planes[2][G::FRAME];
     alignas(16) int z[8][G::PH][G::ZP];                  // [couple of the pass][phase][row - phase + PH - 1]
     alignas(16) EpiSmem<G::NM, NBITS, L> epi;            // epi.curve accumulates the weighted diagonal sums of a frame
-    alignas(16) uint32_t win2[G::N];
+    alignas(16) uint32_t winp[G::N / 2];               // packed window table (umma_prep16p)
     uint16_t couple_tab[G::PASSES][8];                   // (pair << 8) | weight shift (8: y.h, 0: y.l) of each couple
     float gauss[2 * L + 1];
     alignas(8) uint64_t full[2], empty[2], ready[2], sfree[2];
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
     // ---- one-time CTA set-up
     for (int i = tid; i < (int)(sizeof(s.planes) / 16); i += G::THREADS)
         reinterpret_cast<uint4 *>(&s.planes[0][0])[i] = make_uint4(0, 0, 0, 0);
-    imma_win_fill(s.win2, p.window, N, tid, G::THREADS);
+    umma_win_fill_packed(s.winp, p.window, N, tid, G::THREADS);
     for (int i = tid; i < 2 * L + 1; i += G::THREADS) s.gauss[i] = p.gauss[i];
     if (tid < G::PASSES * 8) {      // couple = 32 columns [y.d * x.h | y.d * x.l]: (y, d) of its group, x channel in order
         const int g = tid >> 3, c = tid & 7, y0 = pass_y(g, 0);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(UmmaMGeo<NBITS, L>::THREADS, 1) at_fused_umma_
                 const int i0 = q * 512 + lane * 16;
                 const uint32_t rw[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
                 uint32_t hi[4], lo[4];
-                umma_prep16(rw, mean, s.win2, i0, hi, lo);
+                umma_prep16p(rw, mean, s.winp, N, i0, hi, lo);
                 *reinterpret_cast<uint4 *>(ph + PAD + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(pl + PAD + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 if (G::COPIES == 2) {   // second copy, advanced by 8 bytes: sample i sits at PAD - 8 + i

@@ -96,6 +96,37 @@ __device__ __forceinline__ void umma_prep16(const uint32_t (&rw)[4], int mean, c
         hi[w4] = __byte_perm(t01, t23, 0x7632);
     }
 }
+// The same from a PACKED window table (half the shared-memory reads): word j of a 16-sample chunk c holds 2W of samples
+// 2j (low half) and 2j + 1 (high half); the two halves of every chunk are stored in two arrays so that the lanes' 16-byte
+// reads are contiguous: winp[(h * n / 16 + c) * 4 + (j & 3)], h = j >> 2.  The halves are masked apart here (IDP.2A adds the
+// two 16-bit products of a word, so the other half must be zero).
+__device__ __forceinline__ void umma_win_fill_packed(uint32_t *winp, const int16_t *window, int n, int tid, int nthreads)
+{
+    for (int i = tid; i < n / 2; i += nthreads) {
+        const int c = i >> 3, j = i & 7;
+        winp[((j >> 2) * (n / 16) + c) * 4 + (j & 3)] = ((uint32_t)(2 * (int)window[2 * i]) & 0xFFFFu) | ((uint32_t)(2 * (int)window[2 * i + 1]) << 16);
+    }
+}
+__device__ __forceinline__ void umma_prep16p(const uint32_t (&rw)[4], int mean, const uint32_t *winp, int n, int i0,
+                                             uint32_t (&hi)[4], uint32_t (&lo)[4])
+{
+    const uint32_t k4 = (uint32_t)((256 - mean) & 0xFF) * 0x01010101u;
+    const uint32_t k7 = k4 & 0x7F7F7F7Fu, kM = k4 & 0x80808080u;
+    const uint4 wa = *reinterpret_cast<const uint4 *>(&winp[(i0 >> 4) * 4]);
+    const uint4 wb = *reinterpret_cast<const uint4 *>(&winp[(n / 16 + (i0 >> 4)) * 4]);
+    const uint32_t ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+    for (int w4 = 0; w4 < 4; w4++) {
+        const uint32_t d = sub_bytes(rw[w4], k7, kM);
+        const uint32_t e0 = ww[2 * w4], e1 = ww[2 * w4 + 1];                    // samples (4 w4, 4 w4 + 1), (4 w4 + 2, 4 w4 + 3)
+        const int p0 = dp2a_lo_acc(e0 & 0xFFFFu, d, 0x8000), p1 = dp2a_lo_acc(e0 & 0xFFFF0000u, d, 0x8000);
+        const int p2 = dp2a_hi_acc(e1 & 0xFFFFu, d, 0x8000), p3 = dp2a_hi_acc(e1 & 0xFFFF0000u, d, 0x8000);
+        const uint32_t t01 = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x6251);
+        const uint32_t t23 = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x6251);
+        lo[w4] = __byte_perm(t01, t23, 0x5410) ^ 0x80808080u;
+        hi[w4] = __byte_perm(t01, t23, 0x7632);
+    }
+}
 // the same with the lane's 16 window words (doubled, pre-masked: even samples low half, odd samples high half) in registers
 __device__ __forceinline__ void umma_prep16r(const uint32_t (&rw)[4], int mean, const uint32_t (&wr)[16],
                                              uint32_t (&hi)[4], uint32_t (&lo)[4])
