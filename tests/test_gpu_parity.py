@@ -358,6 +358,24 @@ def test_host_api_and_sharding_match_device_api(loc):
         assert (host[k] == dev[k].cpu().numpy()).all(), k
     assert (host2["lags"] == host["lags"]).all()
     assert (lags == host["lags"]).all() and (cell == host["cell"]).all()
+    # whole correlations_t structs, pinned in and out, 13 chunks rotating over the three slots (copy-in, kernel and copy-out
+    # streams chained by events), twice in a row on the same slots
+    os.environ["AT_CHUNK_FRAMES"] = "400"
+    try:
+        devs = loc.localize_device(adc, heads, want=("lags", "corr", "xy"), struct_corr=True)
+        torch.cuda.synchronize()
+        outp = {"lags": torch.empty((F, 3), dtype=torch.int32).pin_memory(),
+                "corr": torch.empty((F, 3, 95), dtype=torch.int64).pin_memory(),
+                "xy": torch.empty((F, 2), dtype=torch.float32).pin_memory()}
+        for _ in range(2):
+            outp["corr"].zero_()
+            loc.localize_host(pinned, heads_h, want=("lags", "corr", "xy"), out=outp, struct_corr=True)
+            dcorr, hcorr = devs["corr"].cpu().numpy(), outp["corr"].numpy()
+            assert (hcorr[:, :, :94] == dcorr[:, :, :94]).all()      # curves and best_shift; the time stamp differs per call
+            assert (outp["lags"].numpy() == devs["lags"].cpu().numpy()).all()
+            assert (outp["xy"].numpy() == devs["xy"].cpu().numpy()).all()
+    finally:
+        del os.environ["AT_CHUNK_FRAMES"]
 
 
 def test_host_api_config4_tcgen05_chunks():
