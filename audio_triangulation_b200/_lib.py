@@ -73,6 +73,8 @@ def load():
         "at_localize_host": (C.c_int, [ctx, vp, vp, sz, C.POINTER(AtOutputs)]),
         "at_peer_enable": (C.c_int, [ctx, i32]),
         "at_copy_async": (C.c_int, [ctx, vp, vp, sz, vp]),
+        "at_host_alloc": (C.c_int, [ctx, sz, C.POINTER(vp)]),
+        "at_host_free": (C.c_int, [ctx, vp]),
         "at_shared_alloc": (C.c_int, [ctx, sz, C.POINTER(vp), C.c_char_p]),
         "at_shared_open": (C.c_int, [ctx, C.c_char_p, C.POINTER(vp)]),
         "at_shared_close": (C.c_int, [ctx, vp, i32]),

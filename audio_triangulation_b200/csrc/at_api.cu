@@ -438,6 +438,21 @@ extern "C" int at_shared_close(at_context *c, void *d_ptr, int opened)
     return AT_OK;
 }
 
+extern "C" int at_host_alloc(at_context *c, size_t bytes, void **h_ptr)
+{
+    if (!c || !h_ptr || !bytes) return fail(AT_EINVAL, "at_host_alloc: bad argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable));
+    return AT_OK;
+}
+
+extern "C" int at_host_free(at_context *c, void *h_ptr)
+{
+    if (!c) return fail(AT_EINVAL, "at_host_free: null context");
+    if (h_ptr) CU(cudaFreeHost(h_ptr));
+    return AT_OK;
+}
+
 extern "C" int at_copy_async(at_context *c, void *d_dst, const void *d_src, size_t bytes, void *stream)
 {
     if (!c || !d_dst || !d_src) return fail(AT_EINVAL, "at_copy_async: null argument");

@@ -67,9 +67,12 @@ int main(int argc, char **argv)
            (lags1[0] == fresh[0].best_shift && lags1[1] == fresh[1].best_shift && lags1[2] == fresh[2].best_shift) ? "[agree]" : "[MISMATCH]");
 
     /* --- a batch of synthetic frames, host buffers in, results out --- */
-    uint8_t *adc = malloc(F * 3 * BUFFER_SIZE);
-    int32_t *lags = malloc(F * 3 * sizeof *lags), *cell = malloc(F * sizeof *cell), *truth = malloc(F * sizeof *truth);
-    if (!adc || !lags || !cell || !truth) return 2;
+    uint8_t *adc = NULL;                                      /* capture and result buffers: page-locked, copied at the link rate */
+    int32_t *lags = NULL, *cell = NULL, *truth = malloc(F * sizeof *truth);
+    CHECK(at_host_alloc(ctx, F * 3 * BUFFER_SIZE, (void **)&adc));
+    CHECK(at_host_alloc(ctx, F * 3 * sizeof *lags, (void **)&lags));
+    CHECK(at_host_alloc(ctx, F * sizeof *cell, (void **)&cell));
+    if (!truth) return 2;
     double t0 = now_s();
     CHECK(at_synth_host(ctx, 0xA7D10, 0, 0, F, adc, NULL, truth));
     double t1 = now_s();
@@ -84,10 +87,10 @@ int main(int argc, char **argv)
         const int dx = cell[f] % 101 - truth[f] % 101, dy = cell[f] / 101 - truth[f] / 101;
         near += (dx * dx + dy * dy) <= 25;
     }
-    printf("batch        : %zu frames generated in %.2f s; localized in %.3f s (%.2f M frames/s from pageable host memory); "
+    printf("batch        : %zu frames generated in %.2f s; localized in %.3f s (%.2f M frames/s from page-locked host memory); "
            "%.1f %% within 5 cells of the source; %llu kernel launches\n",
            F, t1 - t0, t3 - t2, F / (t3 - t2) / 1e6, 100.0 * near / F, (unsigned long long)at_kernel_launches());
-    free(adc); free(lags); free(cell); free(truth);
+    at_host_free(ctx, adc); at_host_free(ctx, lags); at_host_free(ctx, cell); free(truth);
     at_destroy(ctx);
     return 0;
 }

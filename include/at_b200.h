@@ -222,6 +222,11 @@ int at_shared_close(at_context *ctx, void *d_ptr, int opened /* 1: from at_share
 int at_peer_enable(at_context *ctx, int peer_device);
 /* Asynchronous device-to-device copy on `stream` (copy engine; either pointer may be an at_shared_open mapping). */
 int at_copy_async(at_context *ctx, void *d_dst, const void *d_src, size_t bytes, void *stream);
+/* Page-locked host memory for capture / result buffers: at_localize_host copies such buffers at the link rate (55 GB/s on
+ * PCIe 5 x16) instead of staging pageable memory (replaces the static frame buffers of ref: sample_compute.h:24-38 in a
+ * host harness).  at_host_free releases it. */
+int at_host_alloc(at_context *ctx, size_t bytes, void **h_ptr);
+int at_host_free(at_context *ctx, void *h_ptr);
 
 /* Temporal stage for `n_arrays` independent arrays (ref: sample_compute.h:124-139,
  * correlations.c:38-63): where gate[i] != 0, estimate <- EMA(estimate, fresh) with the array's own
