@@ -253,8 +253,9 @@ int at_pair_max_shift(at_context *ctx, int32_t *out);
  * at_localize_device); d_lags: int32 [F][pairs].  Device pointers, asynchronous on `stream`. */
 int at_admissible_lags_device(at_context *ctx, const int64_t *d_curves, size_t n_frames, int32_t *d_lags, void *stream);
 
-/* GCC-PHAT / FFT variant of the TDOA stage (hand-written radix-2 FFT, no cuFFT), for the direct-vs-FFT crossover
- * study of long frames / wide lag ranges.  NOT a reference algorithm (the reference correlates directly,
+/* GCC-PHAT / FFT variant of the TDOA stage (hand-written, no cuFFT: register-resident radix-8 FFTs forward, one tcgen05
+ * fp16 contraction over the admissible lags backward -- or inverse FFTs with AT_GCC_INVERSE=fft), for the direct-vs-FFT
+ * crossover study of long frames / wide lag ranges.  NOT a reference algorithm (the reference correlates directly,
  * components/correlations.c:9-24): PHAT whitening changes the statistic, only arg-max lags are comparable.
  * Same integer frame preparation, then float32.  d_peak (optional): normalised peak value per pair. */
 int at_gccphat_device(at_context *ctx, const uint8_t *d_adc, const int32_t *d_heads, size_t n_frames,
