@@ -77,6 +77,7 @@ struct at_context {
     // device tables
     float *d_mic_xy = nullptr; uint8_t *d_lut = nullptr; uint8_t *d_cand_idx = nullptr; int32_t *d_cand_cell = nullptr;
     uint8_t *d_cs_idx = nullptr; int32_t *d_cs_cell = nullptr; int32_t *d_cs_grid = nullptr; float2 *d_cell_xy = nullptr;
+    int4 *d_cand_cxy = nullptr;
     int4 *d_peak_tab = nullptr;
     int32_t *d_pair_lmax = nullptr; std::vector<int32_t> h_pair_lmax;   // admissible |lag| per pair
     int16_t *d_window = nullptr; float *d_gauss = nullptr; int32_t *d_delay_q8 = nullptr;
@@ -157,7 +158,7 @@ extern "C" void at_destroy(at_context *c)
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
-                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_spec, c->d_gcc_tw, c->d_gcc_a, c->d_peak_tab, c->d_pair_lmax};
+                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_cand_cxy, c->d_spec, c->d_gcc_tw, c->d_gcc_a, c->d_peak_tab, c->d_pair_lmax};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &h : c->cert_hist) { if (h.ev) cudaEventDestroy(h.ev); if (h.h_count) cudaFreeHost(h.h_count); }
     if (c->h_avg_time) cudaFreeHost(c->h_avg_time);
@@ -266,6 +267,19 @@ static int create_impl(const at_config *cfg, at_context *c)
         CU(cudaMalloc(&c->d_cand_cell, sizeof(int32_t) * c->n_cand));
         CU(cudaMemcpy(c->d_cand_idx, idx.data(), idx.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_cand_cell, first_cell.data(), sizeof(int32_t) * c->n_cand, cudaMemcpyHostToDevice));
+        {   // cell and plane coordinates of every tuple in one 16-byte entry (the search's last step is one load, not two dependent ones)
+            std::vector<float2> xy((size_t)c->n_cells);
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaMemcpy(xy.data(), c->d_cell_xy, sizeof(float2) * xy.size(), cudaMemcpyDeviceToHost));
+            std::vector<int4> cxy((size_t)c->n_cand);
+            for (int t = 0; t < c->n_cand; t++) {
+                int xb, yb;
+                memcpy(&xb, &xy[first_cell[t]].x, 4); memcpy(&yb, &xy[first_cell[t]].y, 4);
+                cxy[t] = make_int4(first_cell[t], xb, yb, 0);
+            }
+            CU(cudaMalloc(&c->d_cand_cxy, sizeof(int4) * cxy.size()));
+            CU(cudaMemcpy(c->d_cand_cxy, cxy.data(), sizeof(int4) * cxy.size(), cudaMemcpyHostToDevice));
+        }
         // the same tuples ordered by (index of pair 0, index of pair 1) with a 2-D offset grid, for
         // the kernels' bounded likelihood search (index bookkeeping only)
         const int NLg = c->n_lags, P = c->n_pairs, T = c->n_cand;
@@ -479,7 +493,7 @@ extern "C" int at_peer_enable(at_context *c, int peer_device)
 static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int kernel, cudaStream_t st)
 {
     p.window = c->d_window; p.gauss = c->d_gauss; p.lut = c->d_lut;
-    p.cand_idx = c->d_cand_idx; p.cand_cell = c->d_cand_cell;
+    p.cand_idx = c->d_cand_idx; p.cand_cell = c->d_cand_cell; p.cand_cxy = c->d_cand_cxy;
     p.cs_idx = c->d_cs_idx; p.cs_cell = c->d_cs_cell; p.cs_grid = c->d_cs_grid; p.peak_tab = c->d_peak_tab;
     p.opaque_four = 4;
     p.cell_xy = c->d_cell_xy;
@@ -529,8 +543,8 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
             }
 #ifdef AT_PROF
             static unsigned long long *d_prof = nullptr;
-            if (!d_prof) CU(cudaMalloc((void **)&d_prof, 32 * 8));
-            CU(cudaMemsetAsync(d_prof, 0, 32 * 8, st));
+            if (!d_prof) CU(cudaMalloc((void **)&d_prof, 40 * 8));
+            CU(cudaMemsetAsync(d_prof, 0, 40 * 8, st));
             p.prof = d_prof;
 #endif
             e = at_launch_fused_umma(sh, p, redo, c->sm_count, st);
@@ -542,11 +556,11 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
             }
 #ifdef AT_PROF
             if (e == cudaSuccess && getenv("AT_PROF_PRINT")) {
-                unsigned long long h[32];
+                unsigned long long h[40];
                 CU(cudaStreamSynchronize(st));
                 CU(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
-                static const char *role[4] = {"mma-issue", "prep", "epi-q0", "epi-q1-3"};
-                for (int r = 0; r < 4; r++) {
+                static const char *role[5] = {"mma-issue", "prep", "epi-q0", "epi-q1-3", "block-epi"};   // block-epi: thread 0 of every group
+                for (int r = 0; r < 5; r++) {
                     fprintf(stderr, "AT_PROF %-9s cycles/frame/SM (summed over the role's warps):", role[r]);
                     for (int k = 0; k < 8; k++) fprintf(stderr, " %8.1f", (double)h[r * 8 + k] / ((double)p.n_frames / c->sm_count));
                     fprintf(stderr, "\n");

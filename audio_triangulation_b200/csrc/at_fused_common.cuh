@@ -190,15 +190,18 @@ __device__ __forceinline__ Best best_of(Best a, Best b)
     return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
 }
 __device__ __forceinline__ Best warp_best(Best x)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        Best y;
-        y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
-        y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
-        x = best_of(x, y);
-    }
-    return x;
+{   // three REDUX instead of five rounds of 64-bit shuffles: maximum of the high words, of the low words among those, lowest index
+    const int hi = (int)(x.v >> 32);
+    const unsigned lo = (unsigned)x.v;
+    const int mh = __reduce_max_sync(0xffffffffu, hi);
+    const bool in1 = hi == mh;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, in1 ? lo : 0u);
+    const bool in2 = in1 && lo == ml;
+    const int mi = __reduce_min_sync(0xffffffffu, in2 ? x.i : 0x7fffffff);
+    Best r;
+    r.v = (long long)(((unsigned long long)(unsigned)mh << 32) | ml);
+    r.i = mi;
+    return r;
 }
 
 // Shared-memory working set of the epilogue.
@@ -215,7 +218,8 @@ struct EpiSmem {
 // curve[][] holds the raw correlation sums.  All THREADS threads of the group call; it synchronises the group with
 // barrier bar_id (0 and THREADS = blockDim.x: the whole CTA, i.e. __syncthreads; a warp-specialised kernel passes its
 // own barrier id and the index of the thread within the group).
-template <int NMICS, int NBITS, int L, int THREADS, int BAR = 0>
+// HAVE_BEST: the caller has already found the first-max lags and stored them in e.best[] (and in p.lags); step (1) is skipped.
+template <int NMICS, int NBITS, int L, int THREADS, int BAR = 0, bool HAVE_BEST = false>
 __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const float *gauss_s,
                                          const AtFusedParams &p, unsigned long long f, int tid = threadIdx.x, int bar_id = BAR)
 {
@@ -224,8 +228,16 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
     constexpr int NWARPS = THREADS / 32;
     const int lane = tid & 31, warp = tid >> 5;
     auto group_sync = [bar_id] { asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(THREADS) : "memory"); };   // bar_id: group-uniform
+#ifdef AT_PROF
+    // role 4 of the cycle account: [arg-max, gate + raw, Gaussian, curve stores, tuple scan, reduction + outputs, classes], thread 0 of the group
+    unsigned long long ep_t = clock64();
+#define EPI_MARK(k) do { if (tid == 0 && p.prof) { const unsigned long long t_ = clock64(); atomicAdd(&p.prof[32 + (k)], t_ - ep_t); ep_t = t_; } } while (0)
+#else
+#define EPI_MARK(k) do { } while (0)
+#endif
 
     // (1) arg-max per pair (correlations.c:20-23): one warp per pair
+    if constexpr (!HAVE_BEST)
     for (int pr = warp; pr < P; pr += NWARPS) {
         Best b = {LLONG_MIN, 0x7fffffff};
         for (int li = lane; li < NL; li += 32) {
@@ -239,6 +251,7 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
         }
     }
     group_sync();
+    EPI_MARK(0);
     if (p.gate && tid == 0) {           // sample_compute.h:124-134
         int tot = 0;
         for (int pr = 0; pr < P; pr++) tot += e.best[pr] * e.best[pr];
@@ -251,6 +264,7 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
     const bool need_gauss = p.corr || p.cell || p.highest || p.xy || p.classes;
     if (!need_gauss) return;
     group_sync();   // raw reads done before the in-place re-weighting
+    EPI_MARK(1);
 
     // (2) Gaussian re-weighting in place (correlations.c:26-33)
     for (int idx = tid; idx < P * NL; idx += THREADS) {
@@ -261,6 +275,7 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
         e.curve[pr][OFF + li] = __float2ll_rz(__fmul_rn(c, gauss_s[d]));
     }
     group_sync();
+    EPI_MARK(2);
     if (p.corr) {
         if (p.corr_struct) {   // struct correlations_t [F][P]: 93 x int64, int best_shift, pad, uint64 last_update
             long long *base = reinterpret_cast<long long *>(p.corr) + f * (unsigned long long)(P * (NL + 2));
@@ -277,17 +292,37 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
             for (int idx = tid; idx < P * NL; idx += THREADS) base[idx] = e.curve[idx / NL][OFF + idx % NL];
         }
     }
+    EPI_MARK(3);
     if (!(p.cell || p.highest || p.xy || p.classes)) return;
 
     // (3) likelihood maximum over the distinct LUT tuples (vga_heatmap.h:96-108); candidates are
     //     sorted by their first row-major cell, so "lowest candidate index" == "first cell".
     Best b = {LLONG_MIN, 0x7fffffff};
-    for (int c = tid; c < p.n_cand; c += THREADS) {
-        long long like = 0;
+    {   // U candidates per turn: their tuple bytes are all requested before the first dependent curve gather
+        constexpr int U = P <= 6 ? 4 : 2;
+        int c = tid;
+        for (; c + (U - 1) * THREADS < p.n_cand; c += U * THREADS) {
+            int ix[U][P];
 #pragma unroll
-        for (int pr = 0; pr < P; pr++) like += e.curve[pr][OFF + p.cand_idx[pr * p.n_cand + c]];
-        if (like > b.v) { b.v = like; b.i = c; }
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int pr = 0; pr < P; pr++) ix[u][pr] = __ldg(&p.cand_idx[pr * p.n_cand + c + u * THREADS]);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                long long like = 0;
+#pragma unroll
+                for (int pr = 0; pr < P; pr++) like += e.curve[pr][OFF + ix[u][pr]];
+                if (like > b.v) { b.v = like; b.i = c + u * THREADS; }
+            }
+        }
+        for (; c < p.n_cand; c += THREADS) {
+            long long like = 0;
+#pragma unroll
+            for (int pr = 0; pr < P; pr++) like += e.curve[pr][OFF + __ldg(&p.cand_idx[pr * p.n_cand + c])];
+            if (like > b.v) { b.v = like; b.i = c; }
+        }
     }
+    EPI_MARK(4);
     b = warp_best(b);
     if (lane == 0) { e.red_v[warp] = b.v; e.red_i[warp] = b.i; }
     group_sync();
@@ -296,13 +331,14 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
         if (lane < NWARPS) { r.v = e.red_v[lane]; r.i = e.red_i[lane]; }
         r = warp_best(r);
         if (lane == 0) {
-            const int cellidx = p.cand_cell[r.i];
+            const int4 cxy = __ldg(&p.cand_cxy[r.i]);                // {first cell of the tuple, x, y}: vga_heatmap.h:52-53, tabulated
             e.red_v[0] = r.v;
-            if (p.cell) p.cell[f] = cellidx;
+            if (p.cell) p.cell[f] = cxy.x;
             if (p.highest) p.highest[f] = r.v;
-            if (p.xy) reinterpret_cast<float2 *>(p.xy)[f] = p.cell_xy[cellidx];   // vga_heatmap.h:52-53, tabulated per cell
+            if (p.xy) reinterpret_cast<float2 *>(p.xy)[f] = make_float2(__int_as_float(cxy.y), __int_as_float(cxy.z));
         }
     }
+    EPI_MARK(5);
     if (p.classes) {   // vga_heatmap.h:111-126, colour codes of lib/vga/vga16_graphics.h:31-34
         group_sync();
         const long long top = e.red_v[0];

@@ -558,7 +558,8 @@ __global__ void __launch_bounds__(UmmaGeo<L, CERT>::THREADS, 1) at_fused_umma_ke
                     }
                     if (!settled) {
                         if (m == 0 && p.stats && (p.cell || p.highest || p.xy || p.classes)) atomicAdd(&p.stats[2], 1ull);   // route: full scan
-                        epilogue<3, 10, L, 128>(epi, s.gauss, p, f, m, bar_a);
+                        if (m < 3) epi.best[m] = m == 0 ? best3[0] : (m == 1 ? best3[1] : best3[2]);      // the group epilogue skips its own arg-max
+                        epilogue<3, 10, L, 128, 0, true>(epi, s.gauss, p, f, m, bar_a);
                     }
                 }
                 named_bar(bar_a, 128);      // curve / part64 are rewritten by the next frame of this set
