@@ -567,7 +567,25 @@ static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int 
                 }
             }
 #endif
-        } else if (at_fused_umma_m_supports(sh)) e = at_launch_fused_umma_m(sh, p, c->sm_count, st);    // 8 mics x 1024 / 4096
+        } else if (at_fused_umma_m_supports(sh)) {                                                    // 8 mics x 1024 / 4096
+#ifdef AT_PROF
+            static unsigned long long *d_prof8 = nullptr;       // only the group epilogue accounts its cycles here (role block-epi)
+            if (!d_prof8) CU(cudaMalloc((void **)&d_prof8, 40 * 8));
+            CU(cudaMemsetAsync(d_prof8, 0, 40 * 8, st));
+            p.prof = d_prof8;
+#endif
+            e = at_launch_fused_umma_m(sh, p, c->sm_count, st);
+#ifdef AT_PROF
+            if (e == cudaSuccess && getenv("AT_PROF_PRINT")) {
+                unsigned long long h[40];
+                CU(cudaStreamSynchronize(st));
+                CU(cudaMemcpy(h, d_prof8, sizeof h, cudaMemcpyDeviceToHost));
+                fprintf(stderr, "AT_PROF block-epi cycles/frame (thread 0 of the group) [arg-max, gate + raw, Gaussian, curve stores, tuple scan, reduction + outputs]:");
+                for (int k = 0; k < 6; k++) fprintf(stderr, " %8.1f", (double)h[32 + k] / (double)p.n_frames);
+                fprintf(stderr, "\n");
+            }
+#endif
+        }
         else return fail(AT_EINVAL, "UMMA kernel has no instantiation for this shape");
     } else if (kernel == AT_KERNEL_IMMA) {
         if (at_fused_imma_supports(sh)) e = at_launch_fused_imma(sh, p, c->sm_count, st);             // warp per frame, 3 mics
