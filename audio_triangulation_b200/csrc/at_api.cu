@@ -77,7 +77,7 @@ struct at_context {
     // device tables
     float *d_mic_xy = nullptr; uint8_t *d_lut = nullptr; uint8_t *d_cand_idx = nullptr; int32_t *d_cand_cell = nullptr;
     uint8_t *d_cs_idx = nullptr; int32_t *d_cs_cell = nullptr; int32_t *d_cs_grid = nullptr; float2 *d_cell_xy = nullptr;
-    int4 *d_cand_cxy = nullptr;
+    int4 *d_cand_cxy = nullptr; uint4 *d_cand_row32 = nullptr;
     int4 *d_peak_tab = nullptr;
     int32_t *d_pair_lmax = nullptr; std::vector<int32_t> h_pair_lmax;   // admissible |lag| per pair
     int16_t *d_window = nullptr; float *d_gauss = nullptr; int32_t *d_delay_q8 = nullptr;
@@ -158,7 +158,7 @@ extern "C" void at_destroy(at_context *c)
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
     void *ptrs[] = {c->d_mic_xy, c->d_lut, c->d_cand_idx, c->d_cand_cell, c->d_window, c->d_gauss, c->d_delay_q8, c->d_scratch,
-                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_cand_cxy, c->d_spec, c->d_gcc_tw, c->d_gcc_a, c->d_peak_tab, c->d_pair_lmax};
+                    c->d_cs_idx, c->d_cs_cell, c->d_cs_grid, c->d_cell_xy, c->d_cand_cxy, c->d_cand_row32, c->d_spec, c->d_gcc_tw, c->d_gcc_a, c->d_peak_tab, c->d_pair_lmax};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &h : c->cert_hist) { if (h.ev) cudaEventDestroy(h.ev); if (h.h_count) cudaFreeHost(h.h_count); }
     if (c->h_avg_time) cudaFreeHost(c->h_avg_time);
@@ -267,6 +267,13 @@ static int create_impl(const at_config *cfg, at_context *c)
         CU(cudaMalloc(&c->d_cand_cell, sizeof(int32_t) * c->n_cand));
         CU(cudaMemcpy(c->d_cand_idx, idx.data(), idx.size(), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(c->d_cand_cell, first_cell.data(), sizeof(int32_t) * c->n_cand, cudaMemcpyHostToDevice));
+        if (c->n_pairs <= 32) {   // one 32-byte row per candidate: two 16-byte loads instead of one byte load per pair
+            std::vector<uint8_t> rows((size_t)c->n_cand * 32, 0);
+            for (int t = 0; t < c->n_cand; t++)
+                for (int p = 0; p < c->n_pairs; p++) rows[(size_t)t * 32 + p] = (uint8_t)keys[t][p];
+            CU(cudaMalloc(&c->d_cand_row32, rows.size()));
+            CU(cudaMemcpy(c->d_cand_row32, rows.data(), rows.size(), cudaMemcpyHostToDevice));
+        }
         {   // cell and plane coordinates of every tuple in one 16-byte entry (the search's last step is one load, not two dependent ones)
             std::vector<float2> xy((size_t)c->n_cells);
             CU(cudaStreamSynchronize(c->stream));
@@ -493,7 +500,7 @@ extern "C" int at_peer_enable(at_context *c, int peer_device)
 static int launch_fused(at_context *c, const AtShape &sh, AtFusedParams &p, int kernel, cudaStream_t st)
 {
     p.window = c->d_window; p.gauss = c->d_gauss; p.lut = c->d_lut;
-    p.cand_idx = c->d_cand_idx; p.cand_cell = c->d_cand_cell; p.cand_cxy = c->d_cand_cxy;
+    p.cand_idx = c->d_cand_idx; p.cand_cell = c->d_cand_cell; p.cand_cxy = c->d_cand_cxy; p.cand_row32 = c->d_cand_row32;
     p.cs_idx = c->d_cs_idx; p.cs_cell = c->d_cs_cell; p.cs_grid = c->d_cs_grid; p.peak_tab = c->d_peak_tab;
     p.opaque_four = 4;
     p.cell_xy = c->d_cell_xy;

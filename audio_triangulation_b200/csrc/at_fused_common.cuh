@@ -298,7 +298,16 @@ __device__ __forceinline__ void epilogue(EpiSmem<NMICS, NBITS, L> &e, const floa
     // (3) likelihood maximum over the distinct LUT tuples (vga_heatmap.h:96-108); candidates are
     //     sorted by their first row-major cell, so "lowest candidate index" == "first cell".
     Best b = {LLONG_MIN, 0x7fffffff};
-    {   // U candidates per turn: their tuple bytes are all requested before the first dependent curve gather
+    if (P > 6 && p.cand_row32) {   // many pairs: a candidate's tuple is one 32-byte row, two 16-byte loads
+        for (int c = tid; c < p.n_cand; c += THREADS) {
+            const uint4 r0 = __ldg(&p.cand_row32[2 * c]), r1 = __ldg(&p.cand_row32[2 * c + 1]);
+            const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            long long like = 0;
+#pragma unroll
+            for (int pr = 0; pr < P; pr++) like += e.curve[pr][OFF + ((w[pr >> 2] >> (8 * (pr & 3))) & 0xFFu)];
+            if (like > b.v) { b.v = like; b.i = c; }
+        }
+    } else {   // U candidates per turn: their tuple bytes are all requested before the first dependent curve gather
         constexpr int U = P <= 6 ? 4 : 2;
         int c = tid;
         for (; c + (U - 1) * THREADS < p.n_cand; c += U * THREADS) {

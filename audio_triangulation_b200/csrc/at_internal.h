@@ -32,6 +32,7 @@ struct AtFusedParams {
     const uint8_t *cand_idx; // [P][n_cand] distinct lag-index tuples of the LUT
     const int32_t *cand_cell;// [n_cand] first row-major cell of each tuple, ascending
     const int4 *cand_cxy;    // [n_cand] {that cell, its x and y (float bits), 0}: cell and coordinates of a tuple in one load
+    const uint4 *cand_row32; // [n_cand][2] the same tuples, one 32-byte row per candidate (pairs beyond P zero): arrays with many pairs
     // the same tuples sorted by (index of pair 0, index of pair 1) for the bounded search:
     const uint8_t *cs_idx;   // [P][n_cand]
     const int32_t *cs_cell;  // [n_cand] first row-major cell of the tuple
