@@ -5,9 +5,9 @@
 // which is a GEMM with a CONSTANT left operand:  Y[128 x cols] = A[128 x 2N] . B[2N x cols],  A = the cos / -sin table
 // (rows = lags, fp16), B = the whitened cross-spectra of (frame, pair) columns, 256 columns per CTA (a group of frames).
 // tcgen05.mma kind::f16 (fp16 operands, fp32 accumulation in TMEM), M128 x N256 x K16, 4 per chunk of 32 bins.
-// CTA = 10 warps: warp 0 streams A tiles (pre-tiled in the UMMA K-major canonical layout) and the group's whitened
-// spectra by bulk copies; warps 1-8 (one thread per column) form G = conj(U_a) U_b for their (frame, pair) and write the
-// B tile; warp 9 issues the MMAs; at the end warps 1-8 read the accumulators (lane = lag) and take the first-max arg-max.
+// CTA = 18 warps: warp 0 streams A tiles (pre-tiled in the UMMA K-major canonical layout) and the group's whitened
+// spectra by bulk copies; warps 1-16 (two threads per column) form G = conj(U_a) U_b for their (frame, pair) and write the
+// B tile; warp 17 issues the MMAs; at the end warps 1-16 read the accumulators (lane = lag) and take the first-max arg-max.
 // Not a reference algorithm (see at_gccphat.cu); checked against the FFT form and a float64 restatement.
 #include <cuda_fp16.h>
 #include <math.h>
@@ -22,7 +22,9 @@ struct GccDftGeo {
     static constexpr int A_TILE = 128 * 2 * CB * 2;  // bytes: 128 lags x 64 k x fp16
     static constexpr int B_TILE = COLS * 2 * CB * 2; // bytes
     static constexpr int UROW = 144;                 // bytes per (frame, mic) row of a spectra tile: 32 half2 + 16 bytes of padding
-    static constexpr int THREADS = 320;
+    static constexpr int CONV_WARPS = 16;              // two threads per column, half of a chunk's bins each
+    static constexpr int MMA_WARP = 1 + CONV_WARPS;
+    static constexpr int THREADS = 32 * (2 + CONV_WARPS);
 };
 
 struct GccDftSmem {
@@ -70,12 +72,12 @@ __global__ void __launch_bounds__(GccDftGeo::THREADS, 1) gcc_dft_kernel(const __
     const unsigned g = blockIdx.x;
 
     if (tid == 0) {
-        for (int k = 0; k < n_in; k++) { mbar_init(&s.in_full[k], 1); mbar_init(&s.in_empty[k], 9); }   // the MMA commit + eight converter warps
-        for (int k = 0; k < 2; k++) { mbar_init(&s.b_full[k], 8); mbar_init(&s.b_empty[k], 1); }
+        for (int k = 0; k < n_in; k++) { mbar_init(&s.in_full[k], 1); mbar_init(&s.in_empty[k], 1 + G::CONV_WARPS); }   // the MMA commit + the converter warps
+        for (int k = 0; k < 2; k++) { mbar_init(&s.b_full[k], G::CONV_WARPS); mbar_init(&s.b_empty[k], 1); }
         mbar_init(&s.acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 9) {
+    if (warp == G::MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s.tmem_base)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(GccDftGeo::THREADS, 1) gcc_dft_kernel(const __
                 if (++si == n_in) { si = 0; use++; }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == G::MMA_WARP) {
         // =================================================================== MMA issue
         constexpr uint32_t IDESC = umma_idesc_f16(G::COLS);
         constexpr uint32_t LBO_A = 16 * 128, LBO_B = (G::COLS / 8) * 128, SBO = 128;    // K-major, no swizzle: 8 x 16 B core matrices
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(GccDftGeo::THREADS, 1) gcc_dft_kernel(const __
         }
     } else {
         // =================================================================== one thread per column: G = conj(U_a) U_b -> B tile; arg-max
-        const int n = tid - 32, fi = n >> ps_log2, p = n & (PS - 1);
+        const int n = (tid - 32) & (G::COLS - 1), qh = (tid - 32) >> 8, fi = n >> ps_log2, p = n & (PS - 1);      // column, half of the chunk
         const unsigned f = g * (unsigned)FG + (unsigned)fi;
         const bool valid = p < P && f < n_frames;
         int ma = 0, mb = 1;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(GccDftGeo::THREADS, 1) gcc_dft_kernel(const __
                 const uint4 *ub = reinterpret_cast<const uint4 *>(ut + (size_t)(fi * n_mics + mb) * G::UROW);
                 uint8_t *dst = &s.b[st][(n >> 3) * 128 + (n & 7) * 16];
 #pragma unroll
-                for (int q = 0; q < G::CB / 4; q++) {          // 4 bins = 8 k values = one 16-byte core-matrix row
+                for (int q = qh * (G::CB / 8); q < (qh + 1) * (G::CB / 8); q++) {      // 4 bins = 8 k values = one 16-byte core-matrix row
                     const uint4 xa = ua[q], xb = ub[q];
                     const uint32_t wa[4] = {xa.x, xa.y, xa.z, xa.w}, wb[4] = {xb.x, xb.y, xb.z, xb.w};
                     uint32_t o[4];
@@ -166,13 +168,13 @@ __global__ void __launch_bounds__(GccDftGeo::THREADS, 1) gcc_dft_kernel(const __
         float *const gnyq = reinterpret_cast<float *>(&s.b[0][0]);      // the B tiles are free by now (acc_full below)
         mbar_wait(&s.acc_full, 0);
         tc_fence_after();
-        gnyq[n] = gn;
-        named_bar(1, 256);
-        const int wq = warp & 3, half = (warp - 1) >> 2, row = wq * 32 + lane;
+        if (qh == 0) gnyq[n] = gn;
+        named_bar(1, 32 * G::CONV_WARPS);
+        const int wq = warp & 3, part = (warp - 1) >> 2, row = wq * 32 + lane;      // lane quarter, quarter of the columns
         const bool rvalid = row <= 2 * L;
         const float sgn = ((row - L) & 1) ? -1.f : 1.f;
-        for (int cb = 0; cb < 128; cb += 16) {
-            const int c0 = half * 128 + cb;
+        for (int cb = 0; cb < 64; cb += 16) {
+            const int c0 = part * 64 + cb;
             uint32_t v[16];
             tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
             tmem_ld_wait();
@@ -188,8 +190,8 @@ __global__ void __launch_bounds__(GccDftGeo::THREADS, 1) gcc_dft_kernel(const __
             if (lane < 16) s.part[wq][c0 + lane] = make_uint2(mykey, (uint32_t)myrow);
         }
         tc_fence_before();
-        named_bar(1, 256);
-        if (valid) {
+        named_bar(1, 32 * G::CONV_WARPS);
+        if (valid && qh == 0) {
             uint32_t bk = 0; int br = 0;
 #pragma unroll
             for (int q = 0; q < 4; q++) { const uint2 e = s.part[q][n]; if (e.x > bk) { bk = e.x; br = (int)e.y; } }     // strict: first maximum
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(GccDftGeo::THREADS, 1) gcc_dft_kernel(const __
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256));
+    if (warp == G::MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256));
 }
 
 } // namespace atk
