@@ -42,10 +42,16 @@
 //   warp 27      one elected lane issues the MMAs of a frame and commits them to two mbarriers
 //                (accumulators ready / planes free);
 //   warps 20-26  frame preparation, one frame each, two staging and two plane buffers per warp: the raw frame arrives
-//                by a 1-D bulk copy (TMA) one frame ahead; DC removal, <<8, window (held in registers: lane l always
-//                prepares samples [16 l, 16 l + 16) of both frame halves; any ring head: unaligned heads are realigned
-//                in registers), digit planes to shared memory;
-//   warps 0-19   five epilogue sets of four warps; TMEM holds five accumulator slots (three in the exact variant).
+//                by a 1-D bulk copy (TMA) one frame ahead; DC removal, <<8, window (held in registers: lane l prepares
+//                samples [16 l, +16) and their mirror image [1008 - 16 l, +16), the window is symmetric, so 16 registers
+//                serve both; any ring head: unaligned heads are realigned in registers), digit planes to shared memory;
+//   warps 0-19   five epilogue sets of four warps (warp w owns TMEM lane quarter w % 4); TMEM holds four accumulator
+//                slots (three in the exact variant) -- a number that does not divide five, so the tensor core works a
+//                frame ahead of every set.  CERT: the quarters exchange two sums per pair through a triple-buffered
+//                array and ONE warp (the role rotates) decides frame n while the set already works on frame n + 1.
+//                EXACT: peak-tuple look-up, for frames of the redo list a one-warp bounded search, else the group
+//                epilogue of at_fused_common.cuh.
+// What bounds it: the shared-memory data pipe (operand fetch 41 % + LSU 56 %), DESIGN.md 4.1.
 #include <limits.h>
 #include <stdlib.h>
 
